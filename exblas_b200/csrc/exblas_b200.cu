@@ -1,0 +1,608 @@
+// exblas_b200.cu -- host side of the C ABI (include/exblas_b200.h) and the blas1.hpp wrappers.
+//
+// Replaces the reference's OpenCL host plumbing for this path:
+//   src/gpu/blas/blas1/ExSUM.cpp:64-209, ExSUM.Launcher.cpp:47-238,
+//   src/gpu/blas/blas1/ExDOT.cpp:69-223, ExDOT.Launcher.cpp:43-199
+// (per-call context / queue / JIT build / whole-vector copy / two kernel launches / blocking
+// read) by a persistent handle: pre-compiled sm_100a kernels, one launch per reduction, a
+// self-cleaning device workspace, chunked H2D streaming for host inputs, and an exact NCCL limb
+// all-reduce for the multi-GPU path (the reference's MPI_Reduce of limbs, cpu ExSUM.cpp:266-273).
+//
+// There is NO CPU fallback: without a CUDA device every compute entry point fails with
+// EXBLAS_B200_ENOGPU / EXBLAS_B200_ECUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/exblas_b200.h"
+#include "reduce_kernel.cuh"
+
+using namespace exb;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (no link-time dependency; inside a torch process this binds to the NCCL that
+// torch already loaded, in a plain C program to the system libnccl.so.2)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ struct Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+struct Id128 { char bytes[128]; };
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.GetUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(api.lib, "ncclCommInitRank");
+        api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+        api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+        api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+    });
+    return api;
+}
+constexpr int kNcclInt64 = 4;   // ncclInt64
+constexpr int kNcclSum = 0;     // ncclSum
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct exblas_b200_handle_s {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;          // stream in use (own or user's)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    cudaEvent_t consumed[2] = {nullptr, nullptr};
+    Workspace* d_ws = nullptr;
+    Result* d_res = nullptr;
+    Result* h_res = nullptr;                // pinned
+    double* d_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][a|b]
+    int64_t stage_elems = 0;
+    int64_t opt_block_threads = 512;
+    int64_t opt_blocks = 0;
+    int64_t opt_host_chunk = (int64_t)1 << 23;
+    void* comm = nullptr;
+    int nranks = 1;
+    int64_t launches = 0;
+    uint32_t last_status = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail_cuda(exblas_b200_handle_t h, cudaError_t e, const char* what) {
+    if (h) h->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return EXBLAS_B200_ECUDA;
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return fail_cuda(h, e__, #call);     \
+    } while (0)
+
+// fpe / early_exit -> expansion size actually run (cpu ExSUM.cpp:72-99, gpu ExSUM.cpp:70-83,
+// ExDOT.cpp:78-89).  Deviation: fpe > 8 is clamped to 8 instead of returning 0.0.
+int effective_fpe(int fpe, int early_exit, int min_fpe) {
+    if (fpe < min_fpe) return 0;
+    if (early_exit) return fpe <= 4 ? 4 : (fpe <= 6 ? 6 : 8);
+    return fpe > 8 ? 8 : fpe;
+}
+
+constexpr int kMaxT = 512;
+constexpr int kUSum = 4;      // 256-bit vectors in flight per thread, ExSUM
+constexpr int kUDot = 2;      // per input stream, ExDOT
+
+typedef void (*kernel_fn)(const ReduceParams);
+
+template <int F, bool EE, bool DOT>
+kernel_fn kernel_ptr() {
+    return exblas_reduce_kernel<F, EE, DOT, (DOT ? kUDot : kUSum), kMaxT>;
+}
+
+template <bool DOT>
+kernel_fn select_kernel(int f, bool ee) {
+    if (ee) {
+        switch (f) {
+            case 4: return kernel_ptr<4, true, DOT>();
+            case 6: return kernel_ptr<6, true, DOT>();
+            default: return kernel_ptr<8, true, DOT>();
+        }
+    }
+    switch (f) {
+        case 0: return kernel_ptr<0, false, DOT>();
+        case 2: return kernel_ptr<2, false, DOT>();
+        case 3: return kernel_ptr<3, false, DOT>();
+        case 4: return kernel_ptr<4, false, DOT>();
+        case 5: return kernel_ptr<5, false, DOT>();
+        case 6: return kernel_ptr<6, false, DOT>();
+        case 7: return kernel_ptr<7, false, DOT>();
+        default: return kernel_ptr<8, false, DOT>();
+    }
+}
+
+// One kernel launch over DEVICE data.  finalize = 0 leaves the partial sum in the workspace.
+int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double* a, const double* b, int64_t n,
+                  int64_t inca, int64_t incb, int finalize, int round_mode) {
+    ReduceParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = a;
+    p.b = b;
+    p.n = n;
+    p.inca = inca;
+    p.incb = incb;
+    p.ws = h->d_ws;
+    p.out = h->d_res;
+    p.finalize = finalize;
+    p.round_mode = round_mode;
+    p.keep = 0;
+
+    int T = (int)h->opt_block_threads;
+    if (n <= (1 << 16)) T = 128;                       // latency regime: small CTAs, little smem to clear
+    const int U = dot ? kUDot : kUSum;
+    const int64_t tile = (int64_t)T * 4 * U;
+
+    // vector body needs unit strides and, for ExDOT, the same 32-byte phase on both streams
+    p.head = 0;
+    p.ntiles = 0;
+    if (inca == 1 && (!dot || incb == 1) && ((uintptr_t)a % 8 == 0) && (!dot || (uintptr_t)b % 8 == 0)) {
+        const int64_t mis_a = (int64_t)(((uintptr_t)a % 32) / 8);
+        const int64_t head = (4 - mis_a) % 4;
+        bool ok = true;
+        if (dot) ok = ((uintptr_t)b % 32) / 8 == (uintptr_t)mis_a;
+        if (ok && n > head) {
+            p.head = head;
+            p.ntiles = (n - head) / tile;
+            if (p.ntiles == 0) p.head = 0;
+        }
+    }
+    int64_t blocks = h->opt_blocks > 0 ? h->opt_blocks : h->num_sms;
+    int64_t want;
+    if (p.ntiles > 0) want = p.ntiles;
+    else want = (n + T - 1) / T;
+    if (want < 1) want = 1;
+    if (blocks > want) blocks = want;
+
+    kernel_fn fn = dot ? select_kernel<true>(f, ee) : select_kernel<false>(f, ee);
+    const size_t smem = (size_t)T * kLimbs * sizeof(long long);
+    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {(void*)&p};
+    CK(cudaLaunchKernel((const void*)fn, dim3((unsigned)blocks), dim3((unsigned)T), args, smem, h->stream));
+    h->launches += 1;
+    return EXBLAS_B200_OK;
+}
+
+bool is_device_pointer(const void* p) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int ensure_stage(exblas_b200_handle_t h, int64_t elems, bool dot) {
+    if (h->stage_elems >= elems && (!dot || h->d_stage[0][1])) return EXBLAS_B200_OK;
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (h->d_stage[i][j]) {
+                cudaFree(h->d_stage[i][j]);
+                h->d_stage[i][j] = nullptr;
+            }
+    h->stage_elems = 0;
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < (dot ? 2 : 1); ++j) CK(cudaMalloc(&h->d_stage[i][j], (size_t)elems * sizeof(double)));
+    h->stage_elems = elems;
+    return EXBLAS_B200_OK;
+}
+
+// Host inputs: chunked H2D copies on the copy stream, overlapped with the reduction of the previous
+// chunk; every chunk adds into the same device accumulator, the last launch publishes.
+int reduce_from_host(exblas_b200_handle_t h, bool dot, int f, bool ee, const double* a, int64_t inca, const double* b,
+                     int64_t incb, int64_t n, int round_mode) {
+    int64_t chunk = h->opt_host_chunk;
+    if (chunk > n) chunk = n;
+    const int64_t max_inc = dot ? (inca > incb ? inca : incb) : inca;
+    const int64_t span = (chunk - 1) * max_inc + 1;            // doubles copied per chunk and stream
+    int rc = ensure_stage(h, span, dot);
+    if (rc) return rc;
+    int k = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += chunk, ++k) {
+        const int64_t cnt = (n - i0 < chunk) ? n - i0 : chunk;
+        const int s = k & 1;
+        if (k >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->consumed[s], 0));
+        CK(cudaMemcpyAsync(h->d_stage[s][0], a + i0 * inca, (size_t)((cnt - 1) * inca + 1) * sizeof(double),
+                           cudaMemcpyHostToDevice, h->copy_stream));
+        if (dot)
+            CK(cudaMemcpyAsync(h->d_stage[s][1], b + i0 * incb, (size_t)((cnt - 1) * incb + 1) * sizeof(double),
+                               cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaEventRecord(h->copied[s], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->copied[s], 0));
+        const int last = (i0 + cnt >= n);
+        rc = launch_reduce(h, dot, f, ee, h->d_stage[s][0], h->d_stage[s][1], cnt, inca, incb, last, round_mode);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->consumed[s], h->stream));
+    }
+    return EXBLAS_B200_OK;
+}
+
+int reduce_any(exblas_b200_handle_t h, bool dot, const double* a, int64_t inca, int64_t offa, const double* b,
+               int64_t incb, int64_t offb, int64_t n, int fpe, int early_exit, int round_mode, bool device_only) {
+    if (!h) return EXBLAS_B200_EINVAL;
+    if (n < 0 || fpe < 0 || inca < 1 || (dot && incb < 1) || offa < 0 || offb < 0) {
+        h->err = "invalid argument (n < 0, fpe < 0, inc < 1 or offset < 0)";
+        return EXBLAS_B200_EINVAL;
+    }
+    if (n > 0 && (!a || (dot && !b))) {
+        h->err = "null data pointer";
+        return EXBLAS_B200_EINVAL;
+    }
+    CK(cudaSetDevice(h->device));
+    const int f = effective_fpe(fpe, early_exit, dot ? 3 : 2);
+    const bool ee = early_exit && f > 0;
+    if (n == 0) {
+        // publish an exact zero without touching the inputs (ExDOT.cpp:70-71 returns 0.0 for Ng <= 0)
+        static const double zero = 0.0;
+        (void)zero;
+        return launch_reduce(h, dot, 0, false, (const double*)h->d_res, (const double*)h->d_res, 0, 1, 1, 1, round_mode);
+    }
+    const double* pa = a + offa;
+    const double* pb = dot ? b + offb : nullptr;
+    const bool dev_a = is_device_pointer(pa);
+    const bool dev_b = dot ? is_device_pointer(pb) : dev_a;
+    if (dev_a && dev_b) return launch_reduce(h, dot, f, ee, pa, pb, n, inca, incb, 1, round_mode);
+    if (device_only) {
+        h->err = "the *_async entry points need device (or managed) pointers";
+        return EXBLAS_B200_EINVAL;
+    }
+    if (dev_a != dev_b) {
+        h->err = "exdot: a and b must both be host or both be device pointers";
+        return EXBLAS_B200_EINVAL;
+    }
+    return reduce_from_host(h, dot, f, ee, pa, inca, pb, incb, n, round_mode);
+}
+
+int fetch_result(exblas_b200_handle_t h, double* result, int64_t* limbs, uint32_t* status) {
+    CK(cudaMemcpyAsync(h->h_res, h->d_res, sizeof(Result), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->last_status = h->h_res->status;
+    if (result) *result = h->h_res->value;
+    if (status) *status = h->h_res->status;
+    if (limbs)
+        for (int j = 0; j < kLimbs; ++j) limbs[j] = h->h_res->limbs[j];
+    return EXBLAS_B200_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int exblas_b200_version(void) { return 100; }
+
+const char* exblas_b200_strerror(int code) {
+    switch (code) {
+        case EXBLAS_B200_OK: return "ok";
+        case EXBLAS_B200_EINVAL: return "invalid argument";
+        case EXBLAS_B200_ECUDA: return "CUDA error";
+        case EXBLAS_B200_ENOGPU: return "no usable CUDA device";
+        case EXBLAS_B200_ENCCL: return "NCCL error";
+        case EXBLAS_B200_ENOMEM: return "out of memory";
+        default: return "unknown error";
+    }
+}
+
+int exblas_b200_create(exblas_b200_handle_t* out, int device) {
+    if (!out) return EXBLAS_B200_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return EXBLAS_B200_ENOGPU;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return EXBLAS_B200_ENOGPU;
+    if (device >= count) return EXBLAS_B200_EINVAL;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return EXBLAS_B200_ECUDA;
+    if (prop.major != 10) {
+        fprintf(stderr, "exblas_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", device,
+                prop.major, prop.minor);
+        return EXBLAS_B200_ENOGPU;
+    }
+    exblas_b200_handle_t h = new exblas_b200_handle_s();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    int rc = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&h->copied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->consumed[i], cudaEventDisableTiming));
+        }
+        CK(cudaMalloc(&h->d_ws, sizeof(Workspace)));
+        CK(cudaMemset(h->d_ws, 0, sizeof(Workspace)));
+        CK(cudaMalloc(&h->d_res, sizeof(Result)));
+        CK(cudaMemset(h->d_res, 0, sizeof(Result)));
+        CK(cudaMallocHost(&h->h_res, sizeof(Result)));
+        return EXBLAS_B200_OK;
+    }();
+    if (rc) {
+        fprintf(stderr, "exblas_b200_create: %s\n", h->err.c_str());
+        exblas_b200_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_destroy(exblas_b200_handle_t h) {
+    if (!h) return EXBLAS_B200_OK;
+    cudaSetDevice(h->device);
+    if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (h->d_stage[i][j]) cudaFree(h->d_stage[i][j]);
+    if (h->d_ws) cudaFree(h->d_ws);
+    if (h->d_res) cudaFree(h->d_res);
+    if (h->h_res) cudaFreeHost(h->h_res);
+    for (int i = 0; i < 2; ++i) {
+        if (h->copied[i]) cudaEventDestroy(h->copied[i]);
+        if (h->consumed[i]) cudaEventDestroy(h->consumed[i]);
+    }
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_set_stream(exblas_b200_handle_t h, void* stream) {
+    if (!h) return EXBLAS_B200_EINVAL;
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t value) {
+    if (!h || !name) return EXBLAS_B200_EINVAL;
+    if (!strcmp(name, "block_threads")) {
+        if (value < 32 || value > kMaxT || value % 32) return EXBLAS_B200_EINVAL;
+        h->opt_block_threads = value;
+    } else if (!strcmp(name, "blocks")) {
+        if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;    // 2048 partials of < 2^52 fit a limb
+        h->opt_blocks = value;
+    } else if (!strcmp(name, "host_chunk_elems")) {
+        if (value < 1024) return EXBLAS_B200_EINVAL;
+        h->opt_host_chunk = value;
+    } else {
+        return EXBLAS_B200_EINVAL;
+    }
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_exsum_async(exblas_b200_handle_t h, const double* d_a, int64_t n, int64_t inca, int64_t offset, int fpe,
+                            int early_exit, int round_mode) {
+    return reduce_any(h, false, d_a, inca, offset, nullptr, 1, 0, n, fpe, early_exit, round_mode, true);
+}
+
+int exblas_b200_exdot_async(exblas_b200_handle_t h, const double* d_a, int64_t inca, int64_t offseta, const double* d_b,
+                            int64_t incb, int64_t offsetb, int64_t n, int fpe, int early_exit, int round_mode) {
+    return reduce_any(h, true, d_a, inca, offseta, d_b, incb, offsetb, n, fpe, early_exit, round_mode, true);
+}
+
+int exblas_b200_fetch(exblas_b200_handle_t h, double* result, int64_t* limbs, uint32_t* status) {
+    if (!h) return EXBLAS_B200_EINVAL;
+    CK(cudaSetDevice(h->device));
+    return fetch_result(h, result, limbs, status);
+}
+
+int exblas_b200_result_ptr(exblas_b200_handle_t h, void** d_result) {
+    if (!h || !d_result) return EXBLAS_B200_EINVAL;
+    *d_result = h->d_res;
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_exsum_limbs(exblas_b200_handle_t h, const double* a, int64_t n, int64_t inca, int64_t offset, int fpe,
+                            int early_exit, int round_mode, int64_t* limbs, double* result) {
+    int rc = reduce_any(h, false, a, inca, offset, nullptr, 1, 0, n, fpe, early_exit, round_mode, false);
+    if (rc) return rc;
+    return fetch_result(h, result, limbs, nullptr);
+}
+
+int exblas_b200_exdot_limbs(exblas_b200_handle_t h, const double* a, int64_t inca, int64_t offseta, const double* b,
+                            int64_t incb, int64_t offsetb, int64_t n, int fpe, int early_exit, int round_mode,
+                            int64_t* limbs, double* result) {
+    int rc = reduce_any(h, true, a, inca, offseta, b, incb, offsetb, n, fpe, early_exit, round_mode, false);
+    if (rc) return rc;
+    return fetch_result(h, result, limbs, nullptr);
+}
+
+int exblas_b200_exsum(exblas_b200_handle_t h, const double* a, int64_t n, int64_t inca, int64_t offset, int fpe,
+                      int early_exit, int round_mode, double* result) {
+    if (!result) return EXBLAS_B200_EINVAL;
+    return exblas_b200_exsum_limbs(h, a, n, inca, offset, fpe, early_exit, round_mode, nullptr, result);
+}
+
+int exblas_b200_exdot(exblas_b200_handle_t h, const double* a, int64_t inca, int64_t offseta, const double* b,
+                      int64_t incb, int64_t offsetb, int64_t n, int fpe, int early_exit, int round_mode,
+                      double* result) {
+    if (!result) return EXBLAS_B200_EINVAL;
+    return exblas_b200_exdot_limbs(h, a, inca, offseta, b, incb, offsetb, n, fpe, early_exit, round_mode, nullptr,
+                                   result);
+}
+
+int exblas_b200_round(const int64_t* limbs, int round_mode, double* result) {
+    if (!limbs || !result) return EXBLAS_B200_EINVAL;
+    long long acc[kLimbs];
+    for (int j = 0; j < kLimbs; ++j) acc[j] = limbs[j];
+    *result = finalize_value(acc, 0, round_mode);
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_normalize(int64_t* limbs, int* negative) {
+    if (!limbs) return EXBLAS_B200_EINVAL;
+    long long acc[kLimbs];
+    for (int j = 0; j < kLimbs; ++j) acc[j] = limbs[j];
+    bool neg = normalize(acc);
+    for (int j = 0; j < kLimbs; ++j) limbs[j] = acc[j];
+    if (negative) *negative = neg ? 1 : 0;
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_merge_limbs(int64_t* dst, const int64_t* src) {
+    if (!dst || !src) return EXBLAS_B200_EINVAL;
+    long long a[kLimbs], b[kLimbs];
+    for (int j = 0; j < kLimbs; ++j) {
+        a[j] = dst[j];
+        b[j] = src[j];
+    }
+    normalize(a);
+    normalize(b);
+    for (int j = 0; j < kLimbs; ++j) a[j] += b[j];
+    normalize(a);
+    for (int j = 0; j < kLimbs; ++j) dst[j] = a[j];
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_nccl_unique_id(void* id128) {
+    if (!id128) return EXBLAS_B200_EINVAL;
+    if (!nccl().ok) return EXBLAS_B200_ENCCL;
+    return nccl().GetUniqueId(id128) == 0 ? EXBLAS_B200_OK : EXBLAS_B200_ENCCL;
+}
+
+int exblas_b200_comm_init(exblas_b200_handle_t h, int nranks, int rank, const void* id128) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return EXBLAS_B200_EINVAL;
+    if (!nccl().ok) {
+        h->err = "libnccl.so.2 could not be loaded";
+        return EXBLAS_B200_ENCCL;
+    }
+    CK(cudaSetDevice(h->device));
+    Id128 id;
+    memcpy(id.bytes, id128, sizeof(id.bytes));
+    int rc = nccl().CommInitRank(&h->comm, nranks, id, rank);
+    if (rc != 0) {
+        h->err = std::string("ncclCommInitRank: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+        h->comm = nullptr;
+        return EXBLAS_B200_ENCCL;
+    }
+    h->nranks = nranks;
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_allreduce_async(exblas_b200_handle_t h, int round_mode) {
+    if (!h) return EXBLAS_B200_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if (h->nranks > 1) {
+        if (!h->comm) {
+            h->err = "exblas_b200_comm_init was not called";
+            return EXBLAS_B200_ENCCL;
+        }
+        // limbs[39] + flag counters[5] are contiguous int64 in the result slot
+        int rc = nccl().AllReduce(h->d_res->limbs, h->d_res->limbs, kLimbs + kFlagSlots, kNcclInt64, kNcclSum, h->comm,
+                                  h->stream);
+        if (rc != 0) {
+            h->err = std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+            return EXBLAS_B200_ENCCL;
+        }
+        h->launches += 1;
+    }
+    exblas_finalize_kernel<<<1, 32, 0, h->stream>>>(h->d_res, round_mode);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_last_status(exblas_b200_handle_t h, uint32_t* status_flags) {
+    if (!h || !status_flags) return EXBLAS_B200_EINVAL;
+    *status_flags = h->last_status;
+    return EXBLAS_B200_OK;
+}
+
+const char* exblas_b200_last_error(exblas_b200_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int64_t exblas_b200_launch_count(exblas_b200_handle_t h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// blas1.hpp drop-in wrappers (same C++ signatures as the reference's include/blas1.hpp:48,74)
+// ------------------------------------------------------------------------------------------------
+namespace {
+exblas_b200_handle_t default_handle() {
+    static exblas_b200_handle_t h = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int rc = exblas_b200_create(&h, -1);
+        if (rc != EXBLAS_B200_OK) {
+            // the reference's GPU path prints and exits when no platform / device is found
+            // (src/gpu/blas/blas1/ExSUM.cpp:98-108)
+            fprintf(stderr, "exblas_b200: cannot create a GPU handle: %s\n", exblas_b200_strerror(rc));
+            exit(EXIT_FAILURE);
+        }
+    });
+    return h;
+}
+int default_round_mode() {
+    const char* e = getenv("EXBLAS_B200_ROUND");
+    return (e && (!strcmp(e, "exact") || !strcmp(e, "1"))) ? EXBLAS_B200_ROUND_EXACT : EXBLAS_B200_ROUND_REFERENCE;
+}
+}  // namespace
+
+double exsum(const int Ng, double* ag, const int inca, const int offset, const int fpe, const bool early_exit,
+             const bool /*parallel: ignored like the reference GPU path, ExSUM.cpp:61*/) {
+    if (fpe < 0) {   // cpu ExSUM.cpp:25-28
+        fprintf(stderr, "Size of floating-point expansion should be a positive number. Preferably, it should be in the interval [2, 8]\n");
+        exit(1);
+    }
+    exblas_b200_handle_t h = default_handle();
+    double r = 0.0;
+    int rc = exblas_b200_exsum(h, ag, Ng < 0 ? 0 : Ng, inca, offset, fpe, early_exit ? 1 : 0, default_round_mode(), &r);
+    if (rc != EXBLAS_B200_OK) {
+        fprintf(stderr, "exsum: %s (%s)\n", exblas_b200_strerror(rc), exblas_b200_last_error(h));
+        exit(EXIT_FAILURE);
+    }
+    return r;
+}
+
+double exdot(const int Ng, double* ag, const int inca, const int offseta, double* bg, const int incb, const int offsetb,
+             const int fpe, const bool early_exit) {
+    if (Ng <= 0) return 0.0;   // ExDOT.cpp:70-71
+    if (fpe < 0) {
+        fprintf(stderr, "Size of floating-point expansion should be a positive number. Preferably, it should be in the interval [3, 8]\n");
+        exit(1);
+    }
+    exblas_b200_handle_t h = default_handle();
+    double r = 0.0;
+    int rc = exblas_b200_exdot(h, ag, inca, offseta, bg, incb, offsetb, Ng, fpe, early_exit ? 1 : 0,
+                               default_round_mode(), &r);
+    if (rc != EXBLAS_B200_OK) {
+        fprintf(stderr, "exdot: %s (%s)\n", exblas_b200_strerror(rc), exblas_b200_last_error(h));
+        exit(EXIT_FAILURE);
+    }
+    return r;
+}

@@ -1,0 +1,322 @@
+// superacc.cuh -- the 39-limb Kulisch superaccumulator used by the B200 ExSUM / ExDOT path.
+//
+// Layout (identical to the reference's GPU layout, src/gpu/blas/blas1/ExSUM.FPE.cl:14-18 and
+// include/common.hpp:43):  39 signed 64-bit limbs, radix 2^52 (12 carry-save bits per limb),
+// f_words = 20, so limb j weighs 2^(52*(j-20)): limb 0 starts at 2^-1040, limb 38 at 2^936.
+// The reference's CPU layout (41 limbs, f_words = 21, superaccumulator.cpp:14-17) is the same
+// array shifted by one limb, so Round() gives the same double on both.
+//
+// What is here:
+//   * normalize()          -- carry propagation to the unique normal form
+//                             (restates Superaccumulator::Normalize, superaccumulator.cpp:138-162)
+//   * round_ref_compat()   -- bit-for-bit restatement of Superaccumulator::Round
+//                             (superaccumulator.cpp:80-134 == ExSUM.FPE.cl:119-162) on this layout;
+//                             NOT always correctly rounded -- it is the
+//                             reference-parity finaliser
+//   * round_exact()        -- true round-to-nearest-even of the accumulator value
+//   * deposit_*()          -- device side: exact split of one double into two signed limb digits
+//                             and a non-atomic read-modify-write of a THREAD-PRIVATE accumulator
+//                             column in shared memory (replaces Accumulate/AccumulateWord/xadd,
+//                             ExSUM.FPE.cl:168-228, which use 64-bit local atomics)
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define EXB_HD __host__ __device__ __forceinline__
+#define EXB_D __device__ __forceinline__
+#else
+#define EXB_HD inline
+#endif
+
+namespace exb {
+
+constexpr int kLimbs = 39;    // BIN_COUNT
+constexpr int kFWords = 20;   // f_words
+constexpr int kDigits = 52;   // digits = 64 - K, K = 12
+constexpr long long kLimbMask = (1ll << kDigits) - 1;
+
+// A double x = +-1.m * 2^(E-1023) with exponent field E has its mantissa LSB at 2^(E-1075).
+// It lies entirely inside the accumulator when E-1075 >= -1040 (E >= 35) and its top digit
+// lands at or below limb 38 (E < 2011, i.e. |x| < 2^988).  This is the reference GPU kernels'
+// domain (outside it they write out of bounds).
+constexpr unsigned kEMin = 35;
+constexpr unsigned kELim = 2011;
+
+// Status flags (OR-ed together), reported through the C ABI.
+enum : unsigned {
+    kStNaN = 1u,         // a NaN was met (input, or product in ExDOT)
+    kStPosInf = 2u,      // +Inf met
+    kStNegInf = 4u,      // -Inf met
+    kStTooLarge = 8u,    // finite |x| >= 2^988: above the 39-limb layout; element dropped
+    kStTooSmall = 16u,   // bits below 2^-1040 were truncated: result no longer exact
+};
+
+// Limb deposits between two normalisations of one accumulator column: each deposit adds a digit
+// of magnitude <= 2^52 to a limb that starts in [0, 2^52), so 2046 deposits keep |limb| < 2^63.
+constexpr int kMaxDepositsPerNormalize = 2046;
+
+// ---------------------------------------------------------------------------------------------
+// host + device: normal form and the two finalisers
+// ---------------------------------------------------------------------------------------------
+
+// Carry-propagate so that limbs 0..37 are in [0, 2^52) and limb 38 keeps the signed remainder.
+// Returns true when the value is negative.  (superaccumulator.cpp:138-162 with imin = 0)
+EXB_HD bool normalize(long long* acc) {
+    long long carry = acc[0] >> kDigits;
+    acc[0] -= carry << kDigits;
+    for (int i = 1; i < kLimbs; ++i) {
+        long long v = acc[i] + carry;
+        carry = v >> kDigits;
+        acc[i] = v - (carry << kDigits);
+    }
+    acc[kLimbs - 1] += (long long)((unsigned long long)carry << kDigits);
+    return carry < 0;
+}
+
+EXB_HD double exb_ldexp(double x, int e) {
+#if defined(__CUDA_ARCH__)
+    return ldexp(x, e);
+#else
+    return std::ldexp(x, e);
+#endif
+}
+
+// Restatement of the reference Round() on normalised limbs (superaccumulator.cpp:80-134).
+// `acc` must already be in normal form; `negative` is normalize()'s return value.
+EXB_HD double round_ref_compat(const long long* acc, bool negative) {
+    int i = kLimbs - 1;
+    while (i >= 0 && acc[i] == 0) --i;                                   // :91-94
+    if (negative) {
+        while (i >= 0 && (acc[i] & kLimbMask) == kLimbMask) --i;         // :95-101
+    }
+    if (i < 0) return 0.0;                                               // :102-104
+    long long hiword = negative ? kLimbMask - acc[i] : acc[i];           // :106 (one's complement)
+    double rounded = (double)hiword;
+    double hi = exb_ldexp(rounded, (i - kFWords) * kDigits);             // :108
+    if (i == 0) return negative ? -hi : hi;                              // :109-111
+    hiword -= (long long)rounded;                                        // :112 (rounded is integral)
+    double mid = exb_ldexp((double)hiword, (i - kFWords) * kDigits);     // :113
+    long long sticky = 0;
+    for (int j = 0; j != i - 1; ++j)                                     // :116-119
+        sticky |= negative ? (1ll << kDigits) - acc[j] : acc[j];
+    long long loword = negative ? (1ll << kDigits) - acc[i - 1] : acc[i - 1];   // :121
+    loword |= (sticky != 0);                                             // :122
+    double lo = exb_ldexp((double)loword, (i - 1 - kFWords) * kDigits);  // :123
+    if (mid != 0) {                                                      // :128-130, mylibm.hpp:156-171
+        double d = mid + lo;
+        long long l;
+#if defined(__CUDA_ARCH__)
+        l = __double_as_longlong(d);
+        l |= (lo != 0.0);
+        d = __longlong_as_double(l);
+#else
+        std::memcpy(&l, &d, 8);
+        l |= (lo != 0.0);
+        std::memcpy(&d, &l, 8);
+#endif
+        lo = d;
+    }
+    hi = hi + lo;                                                        // :132 the only rounding
+    return negative ? -hi : hi;
+}
+
+EXB_HD int exb_clzll(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+
+// Correctly rounded (nearest, ties to even) value of normalised limbs; handles subnormal
+// results and overflow to +-inf.  Not part of the reference; checked against math.fsum / MPFR.
+EXB_HD double round_exact(const long long* acc, bool negative) {
+    unsigned long long m[kLimbs];      // magnitude, 52-bit digits, top digit unbounded
+    if (!negative) {
+        for (int i = 0; i < kLimbs; ++i) m[i] = (unsigned long long)acc[i];
+    } else {
+        long long borrow = 0;
+        for (int i = 0; i < kLimbs - 1; ++i) {
+            long long v = borrow - acc[i];               // in (-2^52 - 1, 0]
+            borrow = v >> kDigits;
+            m[i] = (unsigned long long)(v - borrow * (1ll << kDigits));
+        }
+        m[kLimbs - 1] = (unsigned long long)(borrow - acc[kLimbs - 1]);
+    }
+    int top = kLimbs - 1;
+    while (top >= 0 && m[top] == 0) --top;
+    if (top < 0) return 0.0;
+    const int width = 64 - exb_clzll(m[top]);            // significant bits of the top digit (<= 63)
+    const int P = kDigits * top + width - 1;             // MSB position above the limb-0 LSB
+    const int e = P - kDigits * kFWords;                 // exponent of the MSB
+    // 64-bit window w = bits [P-63, P] of the magnitude (zero filled), sticky = anything below it
+    unsigned long long w = m[top] << (64 - width);
+    int filled = width;
+    bool sticky = false;
+    for (int j = top - 1; j >= 0; --j) {
+        const int room = 64 - filled;
+        if (room >= kDigits) {
+            w |= m[j] << (room - kDigits);
+            filled += kDigits;
+        } else if (room > 0) {
+            w |= m[j] >> (kDigits - room);
+            sticky |= (m[j] & ((1ull << (kDigits - room)) - 1ull)) != 0;
+            filled = 64;
+        } else {
+            sticky |= (m[j] != 0);
+        }
+    }
+    int keep = 53;                                       // result bits; fewer when subnormal
+    if (e < -1022) keep = 53 - (-1022 - e);
+    unsigned long long q = 0;
+    bool round_bit = false;
+    if (keep >= 1) {
+        q = w >> (64 - keep);
+        round_bit = (w >> (63 - keep)) & 1ull;
+        sticky |= (w & ((1ull << (63 - keep)) - 1ull)) != 0;
+    } else if (keep == 0) {
+        round_bit = true;                                // the MSB itself is the round bit
+        sticky |= (w << 1) != 0;
+    } else {
+        sticky = true;                                   // below half of the smallest subnormal
+    }
+    if (round_bit && (sticky || (q & 1ull))) q += 1;
+    double r = exb_ldexp((double)q, (P - keep + 1) - kDigits * kFWords);
+    return negative ? -r : r;
+}
+
+// Final value from limbs + status flags (IEEE semantics for the specials the kernel met).
+EXB_HD double finalize_value(long long* acc, unsigned status, int round_mode) {
+    bool neg = normalize(acc);
+    if ((status & kStNaN) || ((status & kStPosInf) && (status & kStNegInf))) {
+#if defined(__CUDA_ARCH__)
+        return __longlong_as_double(0x7ff8000000000000ll);
+#else
+        return std::nan("");
+#endif
+    }
+    if (status & kStPosInf) return HUGE_VAL;
+    if (status & kStNegInf) return -HUGE_VAL;
+    return round_mode ? round_exact(acc, neg) : round_ref_compat(acc, neg);
+}
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------
+// device: deposits into a thread-private accumulator column
+//
+// Shared-memory layout: limb j of thread t lives at byte address col + j * stride, where
+// col = smem_base + 8 * t and stride = 8 * T (T = blockDim.x, a multiple of 32).  A 64-bit
+// access by lane l of a warp then falls in bank pair (l mod 16) whatever j is, so every
+// warp-wide LDS.64 / STS.64 is conflict free even though each lane indexes a different limb.
+// No atomics are needed because no two threads share a column.  Addresses are 32-bit
+// shared-window addresses and the accesses are explicit ld.shared / st.shared, so the compiler
+// can never demote them to generic loads.
+// ---------------------------------------------------------------------------------------------
+EXB_D unsigned long long lds64(unsigned addr) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+EXB_D void sts64(unsigned addr, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
+// Fast path: x is finite, non-zero and inside the layout (kEMin <= E < kELim).
+//
+// Let J1 = floor((E-35)/52) + 1 and xs = |x| / 2^(52*J1 - 1040), an exponent-field edit.  Then
+// xs is in [2^s, 2^(s+1)) with s = (E-35) mod 52 <= 51, and its LSB is >= 2^-52, so
+//     D1 = rint(xs)            in [0, 2^52]     (digit for limb J1)
+//     D0 = (xs - D1) * 2^52    in [-2^51, 2^51] (digit for limb J1-1), an exact integer.
+// Both come out of the FP64 pipe with the add-a-magic-constant trick: bits(xs + 2^52) - bits(2^52)
+// = D1 and bits(rem + 1.5) - bits(1.5) = rem * 2^52, which keeps the integer pipe (the busier
+// one here) to ~15 instructions per element.  The sign of x is applied to D0 by flipping rem's
+// sign bit and to D1 by a two's-complement negate folded into the 3-input accumulate add.
+EXB_D void deposit_fast(unsigned col, unsigned stride, unsigned lo, unsigned hi) {
+    const unsigned ahi = hi & 0x7fffffffu;
+    const unsigned E = ahi >> 20;
+    const unsigned J1 = __umulhi(E + 17u, 82595525u);            // floor((E+17)/52), in [1, 38]
+    const unsigned xhi = ahi - J1 * (52u << 20) + (1040u << 20);  // exponent field -> s + 1023
+    const double xs = __hiloint2double((int)xhi, (int)lo);
+    const double t = __dadd_rn(xs, 4503599627370496.0);           // 2^52 + D1
+    const double xr = __dsub_rn(t, 4503599627370496.0);           // D1 as a double
+    double rem = __dsub_rn(xs, xr);                               // exact, in [-0.5, 0.5]
+    rem = __hiloint2double(__double2hiint(rem) ^ (int)(hi & 0x80000000u), __double2loint(rem));
+    const double t2 = __dadd_rn(rem, 1.5);
+    const unsigned long long d0 = (unsigned long long)__double_as_longlong(t2) - 0x3FF8000000000000ull;
+    const unsigned m = (unsigned)((int)hi >> 31);                 // all ones when x < 0
+    const unsigned long long tm = (unsigned long long)__double_as_longlong(t) ^ (((unsigned long long)m << 32) | m);
+    // +D1 = bits(t) - K, -D1 = ~bits(t) + K + 1 with K = bits(2^52) = 0x4330000000000000
+    const unsigned long long ksel = ((unsigned long long)(m ? 0x43300000u : 0xBCD00000u) << 32) | (m & 1u);
+    const unsigned a1 = col + J1 * stride;
+    const unsigned a0 = a1 - stride;
+    const unsigned long long v0 = lds64(a0), v1 = lds64(a1);       // distinct limbs: both loads first
+    sts64(a0, v0 + d0);
+    sts64(a1, v1 + tm + ksel);
+}
+
+EXB_D bool in_fast_range(unsigned hi) {
+    return (((hi & 0x7fffffffu) >> 20) - kEMin) < (kELim - kEMin);
+}
+
+// Slow path for everything else: zeros, specials, values outside the layout, and tiny values
+// (E < 35) whose set bits may still all lie at or above 2^-1040.  Returns status flags.
+__device__ __noinline__ unsigned deposit_slow(unsigned col, unsigned stride, unsigned lo, unsigned hi) {
+    const unsigned ahi = hi & 0x7fffffffu;
+    if ((ahi | lo) == 0u) return 0u;                              // +-0
+    const unsigned E = ahi >> 20;
+    if (E == 0x7ffu) return ((ahi & 0xfffffu) | lo) ? kStNaN : ((hi >> 31) ? kStNegInf : kStPosInf);
+    if (E >= kELim) return kStTooLarge;
+    // E < 35: mantissa LSB is below 2^-1040.  Integer value in units of 2^-1040 = m >> sh.
+    unsigned long long mant = ((unsigned long long)(ahi & 0xfffffu) << 32) | lo;
+    unsigned Eeff = E;
+    if (E == 0u) Eeff = 1u; else mant |= (1ull << 52);
+    const unsigned sh = kEMin - Eeff;                             // 1..34
+    unsigned st = 0u;
+    if (mant & ((1ull << sh) - 1ull)) st = kStTooSmall;           // truncated toward zero
+    const unsigned long long v = mant >> sh;                      // < 2^52
+    const unsigned long long d = (hi >> 31) ? (0ull - v) : v;
+    sts64(col, lds64(col) + d);
+    return st;
+}
+
+// Checked deposit of one double (any value).
+EXB_D void deposit(unsigned col, unsigned stride, double x, unsigned& status) {
+    const unsigned lo = (unsigned)__double2loint(x), hi = (unsigned)__double2hiint(x);
+    if (in_fast_range(hi)) deposit_fast(col, stride, lo, hi);
+    else status |= deposit_slow(col, stride, lo, hi);
+}
+
+// Four independent doubles; one range test for all of them (the common case is all-fast).
+EXB_D void deposit4(unsigned col, unsigned stride, double x0, double x1, double x2, double x3, unsigned& status) {
+    const unsigned h0 = (unsigned)__double2hiint(x0), h1 = (unsigned)__double2hiint(x1);
+    const unsigned h2 = (unsigned)__double2hiint(x2), h3 = (unsigned)__double2hiint(x3);
+    if (in_fast_range(h0) & in_fast_range(h1) & in_fast_range(h2) & in_fast_range(h3)) {
+        deposit_fast(col, stride, (unsigned)__double2loint(x0), h0);
+        deposit_fast(col, stride, (unsigned)__double2loint(x1), h1);
+        deposit_fast(col, stride, (unsigned)__double2loint(x2), h2);
+        deposit_fast(col, stride, (unsigned)__double2loint(x3), h3);
+    } else {
+        deposit(col, stride, x0, status);
+        deposit(col, stride, x1, status);
+        deposit(col, stride, x2, status);
+        deposit(col, stride, x3, status);
+    }
+}
+
+// Normalise a thread-private column in place (same normal form as normalize()).
+EXB_D void normalize_column(unsigned col, unsigned stride) {
+    long long carry = 0;
+    unsigned a = col;
+#pragma unroll 1
+    for (int j = 0; j < kLimbs - 1; ++j, a += stride) {
+        const long long v = (long long)lds64(a) + carry;
+        carry = v >> kDigits;
+        sts64(a, (unsigned long long)(v & kLimbMask));
+    }
+    sts64(a, lds64(a) + (unsigned long long)carry);
+}
+#endif  // __CUDACC__
+
+}  // namespace exb

@@ -1,0 +1,138 @@
+/* exblas_b200.h -- C ABI of the B200-native ExSUM / ExDOT path.
+ *
+ * This is the drop-in boundary for the reference's BLAS-1 entry points
+ *     double exsum(int Ng, double* ag, int inca, int offset, int fpe, bool early_exit, bool parallel)
+ *                                                      (reference include/blas1.hpp:48)
+ *     double exdot(int Ng, double* ag, int inca, int offseta, double* bg, int incb, int offsetb,
+ *                  int fpe, bool early_exit)           (reference include/blas1.hpp:74)
+ * implemented for the GPU in src/gpu/blas/blas1/ExSUM.cpp:64-209 and ExDOT.cpp:69-223.
+ * include/blas1.hpp in this repository keeps those two C++ signatures on top of this ABI.
+ *
+ * Plain pointers and sizes only.  Every data pointer may be a host pointer (pageable or pinned)
+ * or a device / managed pointer on the handle's GPU; the library finds out with
+ * cudaPointerGetAttributes.  Host inputs are streamed through device staging buffers in chunks
+ * (the reference copies the whole vector on every call, ExSUM.cpp:126).
+ *
+ * Argument meaning follows the reference's GPU kernels (ExSUM.FPE.cl:252,298-299): `n` elements
+ * a[offset + i*inca], i = 0..n-1.  fpe < 2 (exsum) / fpe < 3 (exdot) selects the
+ * superaccumulator-only kernel; with early_exit the expansion size is bucketed to 4 / 6 / 8 exactly
+ * as ExSUM.cpp:73-79 does; fpe > 8 is treated as 8 (the reference's CPU path returns 0.0 there).
+ * The result does not depend on fpe / early_exit (they are performance knobs).
+ *
+ * All functions return 0 on success or a negative EXBLAS_B200_E* code; they never call exit().
+ * Status flags about the DATA (NaN, Inf, out-of-range) are reported separately, see below.
+ */
+#ifndef EXBLAS_B200_H_
+#define EXBLAS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXBLAS_B200_LIMBS 39          /* reference bin_count, include/common.hpp:43 */
+
+/* round_mode */
+#define EXBLAS_B200_ROUND_REFERENCE 0 /* bit-for-bit the reference's Superaccumulator::Round()
+                                         (superaccumulator.cpp:80-134; not always correctly rounded) */
+#define EXBLAS_B200_ROUND_EXACT 1     /* correctly rounded, nearest-even */
+
+/* error codes */
+#define EXBLAS_B200_OK 0
+#define EXBLAS_B200_EINVAL (-1)       /* bad argument (negative n, fpe < 0, null pointer, inc == 0 ...) */
+#define EXBLAS_B200_ECUDA (-2)        /* a CUDA runtime call failed; see exblas_b200_last_error() */
+#define EXBLAS_B200_ENOGPU (-3)       /* no usable sm_100 device */
+#define EXBLAS_B200_ENCCL (-4)        /* NCCL missing or a NCCL call failed */
+#define EXBLAS_B200_ENOMEM (-5)
+
+/* data status flags (bitwise OR), returned by exblas_b200_last_status() */
+#define EXBLAS_B200_ST_NAN 1u         /* NaN met: value is NaN */
+#define EXBLAS_B200_ST_POSINF 2u      /* +Inf met */
+#define EXBLAS_B200_ST_NEGINF 4u      /* -Inf met */
+#define EXBLAS_B200_ST_TOOLARGE 8u    /* finite |x| (or product) >= 2^988: outside the 39-limb layout, dropped */
+#define EXBLAS_B200_ST_TOOSMALL 16u   /* bits below 2^-1040 truncated: result not exact */
+
+typedef struct exblas_b200_handle_s* exblas_b200_handle_t;
+
+/* Handle: owns the device workspace (global accumulator, result slot, staging buffers), a stream
+ * and, optionally, a NCCL communicator.  Replaces the per-call OpenCL context / queue / JIT of
+ * ExSUM.cpp:86-209 and ExSUM.Launcher.cpp:47-133.  device < 0 means the current device. */
+int exblas_b200_create(exblas_b200_handle_t* handle, int device);
+int exblas_b200_destroy(exblas_b200_handle_t handle);
+
+/* Use `stream` (a cudaStream_t) for all subsequent work of this handle; NULL = handle's own stream. */
+int exblas_b200_set_stream(exblas_b200_handle_t handle, void* stream);
+
+/* Tuning knobs (performance only, never the result): "block_threads" (multiple of 32, <= 512),
+ * "blocks" (0 = one per SM), "host_chunk_elems". */
+int exblas_b200_set_option(exblas_b200_handle_t handle, const char* name, int64_t value);
+
+/* ---- synchronous entry points: the ones a reference binding calls --------------------------- */
+
+/* replaces exsum()  (reference include/blas1.hpp:48; src/gpu/blas/blas1/ExSUM.cpp:64-84) */
+int exblas_b200_exsum(exblas_b200_handle_t handle, const double* a, int64_t n, int64_t inca, int64_t offset,
+                      int fpe, int early_exit, int round_mode, double* result);
+
+/* replaces exdot()  (reference include/blas1.hpp:74; src/gpu/blas/blas1/ExDOT.cpp:69-92) */
+int exblas_b200_exdot(exblas_b200_handle_t handle, const double* a, int64_t inca, int64_t offseta,
+                      const double* b, int64_t incb, int64_t offsetb, int64_t n,
+                      int fpe, int early_exit, int round_mode, double* result);
+
+/* Same reductions, but return the exact sum as normalised limbs (limb j weighs 2^(52*(j-20)); limbs
+ * 0..37 in [0,2^52), limb 38 signed) instead of / in addition to the rounded value.  This is what the
+ * reference's MPI path exchanges (cpu ExSUM.cpp:266-273).  result may be NULL. */
+int exblas_b200_exsum_limbs(exblas_b200_handle_t handle, const double* a, int64_t n, int64_t inca, int64_t offset,
+                            int fpe, int early_exit, int round_mode, int64_t limbs[EXBLAS_B200_LIMBS], double* result);
+int exblas_b200_exdot_limbs(exblas_b200_handle_t handle, const double* a, int64_t inca, int64_t offseta,
+                            const double* b, int64_t incb, int64_t offsetb, int64_t n,
+                            int fpe, int early_exit, int round_mode, int64_t limbs[EXBLAS_B200_LIMBS], double* result);
+
+/* ---- asynchronous, device-resident entry points (what bench.py times as `value`) ------------- */
+
+/* Enqueue the reduction of DEVICE data on the handle's stream and return at once.  The result
+ * (double value, uint32 status, int64 limbs[39]) is left in the handle's device result slot;
+ * fetch it with exblas_b200_fetch() or read it on the device through exblas_b200_result_ptr(). */
+int exblas_b200_exsum_async(exblas_b200_handle_t handle, const double* d_a, int64_t n, int64_t inca, int64_t offset,
+                            int fpe, int early_exit, int round_mode);
+int exblas_b200_exdot_async(exblas_b200_handle_t handle, const double* d_a, int64_t inca, int64_t offseta,
+                            const double* d_b, int64_t incb, int64_t offsetb, int64_t n,
+                            int fpe, int early_exit, int round_mode);
+/* Wait for the stream and copy the result slot to the host.  Any of the outputs may be NULL. */
+int exblas_b200_fetch(exblas_b200_handle_t handle, double* result, int64_t limbs[EXBLAS_B200_LIMBS], uint32_t* status);
+/* Device address of the result slot: { double value; uint32 status; uint32 pad; int64 limbs[39]; } */
+int exblas_b200_result_ptr(exblas_b200_handle_t handle, void** d_result);
+
+/* ---- limb arithmetic on the host (no GPU needed) ------------------------------------------- */
+
+/* Round normalised-or-not limbs to a double (restates Superaccumulator::Round / exact RN-even). */
+int exblas_b200_round(const int64_t limbs[EXBLAS_B200_LIMBS], int round_mode, double* result);
+/* dst += src limb-wise, then normalise dst (Superaccumulator::Accumulate(Superaccumulator&),
+ * superaccumulator.cpp:68-78). */
+int exblas_b200_merge_limbs(int64_t dst[EXBLAS_B200_LIMBS], const int64_t src[EXBLAS_B200_LIMBS]);
+/* Carry-normalise in place; *negative receives the sign (Superaccumulator::Normalize). */
+int exblas_b200_normalize(int64_t limbs[EXBLAS_B200_LIMBS], int* negative);
+
+/* ---- multi-GPU: exact combination of per-rank limbs over NCCL ------------------------------- */
+
+/* Size of a NCCL unique id in bytes and creation of one (rank 0 calls this and broadcasts it). */
+int exblas_b200_nccl_unique_id(void* id128);
+/* Join a communicator of `nranks` ranks (one process per GPU). */
+int exblas_b200_comm_init(exblas_b200_handle_t handle, int nranks, int rank, const void* id128);
+/* All-reduce (integer sum, exact) of the limbs + status left in the result slot by the last
+ * *_async call, then normalise and round on every rank: every rank ends with identical bits.
+ * Replaces MPI_Reduce(MPI_LONG, MPI_SUM) + Round() of cpu ExSUM.cpp:266-273. */
+int exblas_b200_allreduce_async(exblas_b200_handle_t handle, int round_mode);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+int exblas_b200_last_status(exblas_b200_handle_t handle, uint32_t* status_flags);
+const char* exblas_b200_last_error(exblas_b200_handle_t handle);
+const char* exblas_b200_strerror(int code);
+/* Kernels launched by this handle since creation (bench.py reports it as gpu_launches). */
+int64_t exblas_b200_launch_count(exblas_b200_handle_t handle);
+int exblas_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXBLAS_B200_H_ */
