@@ -64,7 +64,7 @@ def load() -> C.CDLL:
         raise ExblasB200Error(
             f"{LIB_PATH} is missing: build it with `python -m exblas_b200.build` "
             "(nvcc, sm_100a).  exblas_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(LIB_PATH)          # RTLD_LOCAL: exsum/exdot must not interpose other libraries
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = ABI / header mismatch
         fn.restype = res
