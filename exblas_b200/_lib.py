@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libexblas_b200.so")
+LIB_PATH = os.environ.get("EXBLAS_B200_LIB") or os.path.join(HERE, "libexblas_b200.so")   # env override: tuning builds only
 
 LIMBS = 39
 ROUND_REFERENCE = 0

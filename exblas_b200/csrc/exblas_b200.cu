@@ -24,6 +24,25 @@
 
 using namespace exb;
 
+// launch-shape constants (compile-time so that registers per thread can be bounded)
+#ifndef EXB_MAXT
+#define EXB_MAXT 512
+#endif
+constexpr int kMaxT = EXB_MAXT;   // largest CTA (bounds registers per thread: 65536 / kMaxT)
+
+// 256-bit vectors in flight per thread and input stream.  Measured on B200 (profiles/): the direct
+// and small-expansion kernels want a deep window (DRAM latency under load is long), the large
+// expansions need the registers for a[F][2] instead.
+constexpr int vectors_in_flight(int f, bool ee, bool dot) {
+#ifdef EXB_USUM
+    return dot ? EXB_UDOT : EXB_USUM;
+#else
+    if (dot) return (f <= 4 && !ee) ? 4 : 2;
+    if (ee) return 4;
+    return f <= 2 ? 8 : (f <= 4 ? 6 : 4);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // NCCL through dlopen (no link-time dependency; inside a torch process this binds to the NCCL that
 // torch already loaded, in a plain C program to the system libnccl.so.2)
@@ -71,8 +90,7 @@ constexpr int kNcclSum = 0;     // ncclSum
 struct exblas_b200_handle_s {
     int device = 0;
     int num_sms = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;          // stream in use (own or user's)
+    cudaStream_t stream = nullptr;          // stream in use: the legacy default stream (0) or the user's
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr};
     cudaEvent_t consumed[2] = {nullptr, nullptr};
@@ -81,9 +99,10 @@ struct exblas_b200_handle_s {
     Result* h_res = nullptr;                // pinned
     double* d_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][a|b]
     int64_t stage_elems = 0;
-    int64_t opt_block_threads = 512;
+    int64_t opt_block_threads = kMaxT;
     int64_t opt_blocks = 0;
     int64_t opt_host_chunk = (int64_t)1 << 23;
+    int64_t opt_adaptive = 1;
     void* comm = nullptr;
     int nranks = 1;
     int64_t launches = 0;
@@ -111,15 +130,11 @@ int effective_fpe(int fpe, int early_exit, int min_fpe) {
     return fpe > 8 ? 8 : fpe;
 }
 
-constexpr int kMaxT = 512;
-constexpr int kUSum = 4;      // 256-bit vectors in flight per thread, ExSUM
-constexpr int kUDot = 2;      // per input stream, ExDOT
-
 typedef void (*kernel_fn)(const ReduceParams);
 
 template <int F, bool EE, bool DOT>
 kernel_fn kernel_ptr() {
-    return exblas_reduce_kernel<F, EE, DOT, (DOT ? kUDot : kUSum), kMaxT>;
+    return exblas_reduce_kernel<F, EE, DOT, vectors_in_flight(F, EE, DOT), kMaxT>;
 }
 
 template <bool DOT>
@@ -158,10 +173,11 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     p.finalize = finalize;
     p.round_mode = round_mode;
     p.keep = 0;
+    p.adaptive = h->opt_adaptive ? 1 : 0;
 
     int T = (int)h->opt_block_threads;
     if (n <= (1 << 16)) T = 128;                       // latency regime: small CTAs, little smem to clear
-    const int U = dot ? kUDot : kUSum;
+    const int U = vectors_in_flight(f, ee, dot);
     const int64_t tile = (int64_t)T * 4 * U;
 
     // vector body needs unit strides and, for ExDOT, the same 32-byte phase on both streams
@@ -339,9 +355,8 @@ int exblas_b200_create(exblas_b200_handle_t* out, int device) {
     h->num_sms = prop.multiProcessorCount;
     int rc = [&]() -> int {
         CK(cudaSetDevice(device));
-        CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        h->stream = h->own_stream;
+        h->stream = nullptr;                    // legacy default stream, ordered with other default-stream work
         for (int i = 0; i < 2; ++i) {
             CK(cudaEventCreateWithFlags(&h->copied[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->consumed[i], cudaEventDisableTiming));
@@ -376,7 +391,6 @@ int exblas_b200_destroy(exblas_b200_handle_t h) {
         if (h->copied[i]) cudaEventDestroy(h->copied[i]);
         if (h->consumed[i]) cudaEventDestroy(h->consumed[i]);
     }
-    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return EXBLAS_B200_OK;
@@ -384,7 +398,7 @@ int exblas_b200_destroy(exblas_b200_handle_t h) {
 
 int exblas_b200_set_stream(exblas_b200_handle_t h, void* stream) {
     if (!h) return EXBLAS_B200_EINVAL;
-    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    h->stream = (cudaStream_t)stream;
     return EXBLAS_B200_OK;
 }
 
@@ -396,6 +410,8 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "blocks")) {
         if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;    // 2048 partials of < 2^52 fit a limb
         h->opt_blocks = value;
+    } else if (!strcmp(name, "adaptive")) {
+        h->opt_adaptive = value != 0;
     } else if (!strcmp(name, "host_chunk_elems")) {
         if (value < 1024) return EXBLAS_B200_EINVAL;
         h->opt_host_chunk = value;

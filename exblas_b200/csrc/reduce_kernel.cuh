@@ -56,6 +56,7 @@ struct ReduceParams {
     int finalize;                        // 1: publish value/limbs/status and reset workspace
     int round_mode;                      // 0 reference Round(), 1 exact RN-even
     int keep;                            // 1: do not reset the accumulator after publishing
+    int adaptive;                        // 1: bypass the expansion while it thrashes (performance only)
 };
 
 EXB_D Vec4 ldg256(const double* p) {
@@ -70,62 +71,82 @@ EXB_D bool nonzero_bits(double x) {
     return (((unsigned)__double2hiint(x) & 0x7fffffffu) | (unsigned)__double2loint(x)) != 0u;
 }
 
-// One element through the expansion, starting at level `first`.  Returns the residual.
-// Knuth TwoSum, un-contracted (ExSUM.FPE.cl:27-32).  With EE the walk stops as soon as no lane
-// of the warp (UNIFORM) or this thread (!UNIFORM) has a non-zero residual.
+// ---- per-thread state --------------------------------------------------------------------------
+// (col, stride) of the private accumulator column, status flags, and kM independent expansions
+// a[level][m] in registers.  Two expansions per thread give the FP64 pipe independent TwoSum
+// chains to overlap (elements 0,2 of a vector feed expansion 0, elements 1,3 expansion 1); the
+// exact sum does not care how summands are distributed over expansions.
+constexpr int kM = 2;
+
+// Knuth TwoSum, un-contracted (ExSUM.FPE.cl:27-32): a + x = r + s exactly; a <- r, x <- s.
+EXB_D void two_sum(double& a, double& x) {
+    const double r = __dadd_rn(a, x);
+    const double z = __dsub_rn(r, a);
+    const double s = __dadd_rn(__dsub_rn(a, __dsub_rn(r, z)), __dsub_rn(x, z));
+    a = r;
+    x = s;
+}
+
+// Four summands through the expansion levels [first, F), level by level so that four chains are in
+// flight.  With EE the walk stops at the first level after which no lane of the warp (UNIFORM) /
+// this thread (!UNIFORM) holds a non-zero residual: one vote per level per four elements, taken
+// on the integer bit patterns (no FP64-pipe compare, no divergence).  Residuals come back in x[].
 template <int F, bool EE, bool UNIFORM>
-EXB_D double fpe_push(double (&a)[F > 0 ? F : 1], double x, int first = 0) {
+EXB_D void fpe_push4(double (&a)[F > 0 ? F : 1][kM], double (&x)[4], int first) {
 #pragma unroll
     for (int i = 0; i < F; ++i) {
         if (i < first) continue;
-        const double r = __dadd_rn(a[i], x);
-        const double z = __dsub_rn(r, a[i]);
-        const double s = __dadd_rn(__dsub_rn(a[i], __dsub_rn(r, z)), __dsub_rn(x, z));
-        a[i] = r;
-        x = s;
+        two_sum(a[i][0], x[0]);
+        two_sum(a[i][1], x[1]);
+        two_sum(a[i][0], x[2]);
+        two_sum(a[i][1], x[3]);
         if (EE && i + 1 < F) {
+            const unsigned any = ((unsigned)__double2hiint(x[0]) | (unsigned)__double2hiint(x[1]) |
+                                  (unsigned)__double2hiint(x[2]) | (unsigned)__double2hiint(x[3])) << 1 |
+                                 ((unsigned)__double2loint(x[0]) | (unsigned)__double2loint(x[1]) |
+                                  (unsigned)__double2loint(x[2]) | (unsigned)__double2loint(x[3]));
             if (UNIFORM) {
-                if (!__any_sync(0xffffffffu, nonzero_bits(x))) break;
+                if (!__any_sync(0xffffffffu, any != 0u)) break;
             } else {
-                if (!nonzero_bits(x)) break;
+                if (any == 0u) break;
             }
         }
     }
-    return x;
 }
 
-// ---- per-thread state: (col, stride) of the private accumulator column, status flags, and the
-// expansion a[F].  Everything is passed by reference into force-inlined helpers so that it stays
-// in registers (a struct with out-of-line members would be spilled to local memory).
-
-// One summand (any double).  No lane leaves early: the warp-uniform early-exit votes inside
-// fpe_push must be reached by every lane, so special values are diverted and replaced by 0.
-template <int F, bool EE, bool UNIFORM>
-EXB_D void add_value(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1], unsigned& status, double x) {
-    if (F == 0) {
-        deposit(col, stride, x, status);
-    } else {
-        const unsigned hi = (unsigned)__double2hiint(x);
-        if ((hi & 0x7fffffffu) >= (kELim << 20)) {             // Inf / NaN / too large: keep out of the FPE
-            status |= deposit_slow(col, stride, (unsigned)__double2loint(x), hi);
-            x = 0.0;
+// Residuals that fell off the last level go to the superaccumulator column.  Returns how many.
+EXB_D int deposit_residuals(unsigned col, unsigned stride, const double (&x)[4], unsigned& status) {
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (nonzero_bits(x[k])) {
+            deposit(col, stride, x[k], status);
+            ++cnt;
         }
-        const double r = fpe_push<F, EE, UNIFORM>(a, x, 0);
-        if (nonzero_bits(r)) deposit(col, stride, r, status);
     }
+    return cnt;
 }
 
-// The error term of a product enters the expansion lower down (ExDOT.FPE.cl:254-258,
-// ExDOT.FPE.EX.4.cl: level 1 with early exit).
+// Four ordinary inputs (any doubles) through the expansion.  No lane leaves early (the votes in
+// fpe_push4 must be reached by all lanes): Inf / NaN / |x| >= 2^988 are diverted and replaced by 0.
 template <int F, bool EE, bool UNIFORM>
-EXB_D void add_error(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1], unsigned& status, double e) {
-    if (F == 0) {
-        deposit(col, stride, e, status);
-    } else {
-        constexpr int first = EE ? (F > 1 ? 1 : 0) : (F > 3 ? F - 3 : 0);
-        const double r = fpe_push<F, EE, UNIFORM>(a, e, first);
-        if (nonzero_bits(r)) deposit(col, stride, r, status);
+EXB_D int add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][kM], unsigned& status, double (&x)[4]) {
+    const unsigned h0 = (unsigned)__double2hiint(x[0]) & 0x7fffffffu, h1 = (unsigned)__double2hiint(x[1]) & 0x7fffffffu;
+    const unsigned h2 = (unsigned)__double2hiint(x[2]) & 0x7fffffffu, h3 = (unsigned)__double2hiint(x[3]) & 0x7fffffffu;
+    if (max(max(h0, h1), max(h2, h3)) >= (kELim << 20)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned hi = (unsigned)__double2hiint(x[k]);
+            if ((hi & 0x7fffffffu) >= (kELim << 20)) {
+                status |= deposit_slow(col, stride, (unsigned)__double2loint(x[k]), hi);
+                x[k] = 0.0;
+            }
+        }
     }
+    fpe_push4<F, EE, UNIFORM>(a, x, 0);
+    const unsigned any = (unsigned)nonzero_bits(x[0]) | (unsigned)nonzero_bits(x[1]) | (unsigned)nonzero_bits(x[2]) |
+                         (unsigned)nonzero_bits(x[3]);
+    return any ? deposit_residuals(col, stride, x, status) : 0;
 }
 
 // Products that are zero, special, too large, or so small that TwoProd may be inexact.
@@ -137,29 +158,81 @@ __device__ __noinline__ unsigned product_slow(unsigned col, unsigned stride, dou
     if (xz || yz) return 0u;                                       // exact zero product
     const unsigned ph = (unsigned)__double2hiint(p) & 0x7fffffffu;
     if (ph >= (kELim << 20)) return kStTooLarge;                   // finite operands, product >= 2^988
-    // tiny product (|p| < 2^-935).  The FMA error term is exact iff the true error's LSB,
-    // 2^(Ex-1075 + Ey-1075), is representable (>= 2^-1074); otherwise bits were lost.
+    // Tiny product (|p| < 2^-935, or underflowed): TwoProd may have lost bits, so redo it in exact
+    // integer arithmetic.  x = mx * 2^(Ex-1075), y likewise; P = mx*my (<= 106 bits) sits at bit
+    // position pos = Ex + Ey - 2150 + 1040 <= 0 relative to the accumulator LSB (2^-1040).
+    unsigned long long mx = ((unsigned long long)(xh & 0xfffffu) << 32) | (unsigned)__double2loint(x);
+    unsigned long long my = ((unsigned long long)(yh & 0xfffffu) << 32) | (unsigned)__double2loint(y);
+    int ex = (int)(xh >> 20), ey = (int)(yh >> 20);
+    if (ex == 0) ex = 1; else mx |= 1ull << 52;
+    if (ey == 0) ey = 1; else my |= 1ull << 52;
+    unsigned __int128 P = (unsigned __int128)mx * my;
+    const int pos = ex + ey - 2150 + 1040;
     unsigned st = 0u;
-    const unsigned ex = (xh >> 20) ? (xh >> 20) : 1u, ey = (yh >> 20) ? (yh >> 20) : 1u;
-    if (ex + ey < 1076u) st |= kStTooSmall;
-    deposit(col, stride, p, st);                                   // flags kStTooSmall itself if it truncates
-    deposit(col, stride, e, st);
+    if (pos < 0) {
+        const int sh = -pos;
+        if (sh >= 128) {
+            if (P != 0) st |= kStTooSmall;
+            P = 0;
+        } else {
+            if (P & ((((unsigned __int128)1) << sh) - 1)) st |= kStTooSmall;   // truncated toward zero
+            P >>= sh;
+        }
+    } else {
+        P <<= pos;                                                             // pos is 0 here at most a few bits
+    }
+    const bool neg = ((unsigned)__double2hiint(x) ^ (unsigned)__double2hiint(y)) >> 31;
+    unsigned a0 = col;
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j, a0 += stride) {
+        const unsigned long long d = (unsigned long long)(P & (unsigned __int128)kLimbMask);
+        P >>= kDigits;
+        if (d) sts64(a0, neg ? lds64(a0) - d : lds64(a0) + d);
+    }
     return st;
 }
 
+// Four products: TwoProductFMA (ExDOT.FPE.cl:25-29), then p through all levels and the error terms
+// through the lower levels (ExDOT.FPE.cl:254-258: level F-3; ExDOT.FPE.EX.4.cl: level 1 with early
+// exit).  F == 0: both parts are deposited directly (ExDOT.Superacc.cl:244-253).
 template <int F, bool EE, bool UNIFORM>
-EXB_D void add_product(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1], unsigned& status, double x, double y) {
-    double p = __dmul_rn(x, y);
-    double e = __fma_rn(x, y, -p);                                 // TwoProductFMA, ExDOT.FPE.cl:25-29
-    const unsigned ph = (unsigned)__double2hiint(p) & 0x7fffffffu;
-    // TwoProd is exact and both parts lie inside the layout when 2^-935 <= |p| < 2^988
-    if (((ph >> 20) - 88u) >= (kELim - 88u)) {
-        status |= product_slow(col, stride, x, y, p, e);
-        p = 0.0;
-        e = 0.0;
+EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][kM], unsigned& status,
+                   const double (&x)[4], const double (&y)[4]) {
+    double p[4], e[4];
+    unsigned worst = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        p[k] = __dmul_rn(x[k], y[k]);
+        e[k] = __fma_rn(x[k], y[k], -p[k]);
+        // TwoProd is exact and both parts lie inside the layout when 2^-935 <= |p| < 2^988
+        worst = max(worst, ((((unsigned)__double2hiint(p[k]) & 0x7fffffffu) >> 20) - 88u));
     }
-    add_value<F, EE, UNIFORM>(col, stride, a, status, p);
-    add_error<F, EE, UNIFORM>(col, stride, a, status, e);
+    if (worst >= (kELim - 88u)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((((((unsigned)__double2hiint(p[k]) & 0x7fffffffu) >> 20) - 88u)) >= (kELim - 88u)) {
+                status |= product_slow(col, stride, x[k], y[k], p[k], e[k]);
+                p[k] = 0.0;
+                e[k] = 0.0;
+            }
+        }
+    }
+    if (F == 0) {
+        deposit4(col, stride, p[0], p[1], p[2], p[3], status);
+        deposit4(col, stride, e[0], e[1], e[2], e[3], status);     // zeros take the (cheap) slow path
+        return 0;
+    }
+    int cnt = 0;
+    fpe_push4<F, EE, UNIFORM>(a, p, 0);
+    unsigned any = (unsigned)nonzero_bits(p[0]) | (unsigned)nonzero_bits(p[1]) | (unsigned)nonzero_bits(p[2]) |
+                   (unsigned)nonzero_bits(p[3]);
+    if (any) cnt += deposit_residuals(col, stride, p, status);
+    constexpr int first = EE ? (F > 1 ? 1 : 0) : (F > 3 ? F - 3 : 0);
+    fpe_push4<F, EE, UNIFORM>(a, e, first);
+    any = (unsigned)nonzero_bits(e[0]) | (unsigned)nonzero_bits(e[1]) | (unsigned)nonzero_bits(e[2]) |
+          (unsigned)nonzero_bits(e[3]);
+    if (any) cnt += deposit_residuals(col, stride, e, status);
+    return cnt;
 }
 
 // Sum one limb row over all T columns; result valid in lane 0.
@@ -170,6 +243,13 @@ EXB_D long long row_sum(unsigned row_addr, unsigned T, unsigned lane) {
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     return s;
 }
+
+// Thrash control for the expansion (performance only; the sum is exact either way).  When most
+// elements fall off the last level -- data whose dynamic range exceeds what F doubles can hold,
+// e.g. log-uniform over 2^+-332 -- the TwoSum walk is pure overhead, so the warp bypasses the
+// expansion and deposits directly for `kBypassTiles` tiles, then probes the expansion again.
+constexpr int kBypassTiles = 32;
+constexpr int kBypassMax = 4096;
 
 template <int F, bool EE, bool DOT, int U, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReduceParams prm) {
@@ -186,58 +266,79 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
     // columns are thread-private: no barrier needed before use
 
     unsigned status = 0;
-    double a[F > 0 ? F : 1];
+    double a[F > 0 ? F : 1][kM];
 #pragma unroll
-    for (int i = 0; i < (F > 0 ? F : 1); ++i) a[i] = 0.0;
+    for (int i = 0; i < (F > 0 ? F : 1); ++i)
+#pragma unroll
+        for (int m = 0; m < kM; ++m) a[i][m] = 0.0;
 
     constexpr int kDepPerElem = DOT ? 2 : 1;               // at most one deposit per summand
     constexpr int kDepPerTile = 4 * U * kDepPerElem;
     const long long TILE = (long long)T * 4 * U;
 
     // ---------------- vector body: full tiles, 256-bit loads, rolling prefetch ----------------
-    if (prm.ntiles > 0) {
-        const double* pa = prm.a + prm.head + (long long)tid * 4;
-        const double* pb = DOT ? prm.b + prm.head + (long long)tid * 4 : nullptr;
+    if (prm.ntiles > 0 && (long long)blockIdx.x < prm.ntiles) {
+        // this CTA owns tiles blockIdx.x, blockIdx.x + grid, ...: `iters` of them
+        const unsigned iters = (unsigned)((prm.ntiles - 1 - blockIdx.x) / gridDim.x) + 1u;
+        const long long tile_step = (long long)gridDim.x * TILE;               // elements between my tiles
+        const double* pa = prm.a + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4;
+        const double* pb = DOT ? prm.b + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4 : nullptr;
+        const long long vstep = (long long)T * 4;                               // elements between my vectors
         Vec4 va[U];
         Vec4 vb[DOT ? U : 1];
-        long long tile = blockIdx.x;
-        if (tile < prm.ntiles) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                va[u] = ldg256(pa + tile * TILE + (long long)u * T * 4);
-                if (DOT) vb[u] = ldg256(pb + tile * TILE + (long long)u * T * 4);
-            }
+        for (int u = 0; u < U; ++u) {
+            va[u] = ldg256(pa + u * vstep);
+            if (DOT) vb[u] = ldg256(pb + u * vstep);
         }
         int since_norm = 0;
-        while (tile < prm.ntiles) {
-            const long long next = tile + gridDim.x;
-            const bool has_next = next < prm.ntiles;
+        int bypass = 0, backoff = kBypassTiles;
+        for (unsigned it = 0; it < iters; ++it) {
+            pa += tile_step;
+            if (DOT) pb += tile_step;
+            const bool has_next = it + 1 < iters;
+            const bool direct = (F == 0) || (prm.adaptive && bypass > 0);
+            int deposits = 0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const Vec4 x = va[u];
-                Vec4 y;
-                if (DOT) y = vb[u];
-                if (has_next) {
-                    va[u] = ldg256(pa + next * TILE + (long long)u * T * 4);
-                    if (DOT) vb[u] = ldg256(pb + next * TILE + (long long)u * T * 4);
-                }
-                if (DOT) {
-                    add_product<F, EE, true>(col, stride, a, status, x.x, y.x);
-                    add_product<F, EE, true>(col, stride, a, status, x.y, y.y);
-                    add_product<F, EE, true>(col, stride, a, status, x.z, y.z);
-                    add_product<F, EE, true>(col, stride, a, status, x.w, y.w);
-                } else if (F == 0) {
-                    deposit4(col, stride, x.x, x.y, x.z, x.w, status);
+                double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                double y[4];
+                if (DOT) { y[0] = vb[u].x; y[1] = vb[u].y; y[2] = vb[u].z; y[3] = vb[u].w; }
+                if (direct) {
+                    if (DOT) {
+                        double none[1][kM];
+                        mul_add4<0, false, true>(col, stride, none, status, x, y);
+                    } else {
+                        deposit4(col, stride, x[0], x[1], x[2], x[3], status);
+                    }
                 } else {
-                    add_value<F, EE, true>(col, stride, a, status, x.x);
-                    add_value<F, EE, true>(col, stride, a, status, x.y);
-                    add_value<F, EE, true>(col, stride, a, status, x.z);
-                    add_value<F, EE, true>(col, stride, a, status, x.w);
+                    if (DOT) deposits += mul_add4<F, EE, true>(col, stride, a, status, x, y);
+                    else deposits += add4<F, EE, true>(col, stride, a, status, x);
+                }
+                // refill this slot for the next tile (consumed one full iteration from now)
+                if (has_next) {
+                    va[u] = ldg256(pa + u * vstep);
+                    if (DOT) vb[u] = ldg256(pb + u * vstep);
                 }
             }
-            tile = next;
+            if (F > 0 && prm.adaptive) {
+                if (bypass > 0) {
+                    --bypass;
+                } else {
+                    // Warp-uniform decision.  A deposit is an out-of-line, divergent call: once more than
+                    // ~1.5 % of the warp's summands need one, nearly every vector step pays for it and
+                    // depositing everything directly is cheaper.  Back off exponentially while it lasts.
+                    const int total = __reduce_add_sync(0xffffffffu, deposits);
+                    if (total * 64 >= 32 * kDepPerTile) {
+                        bypass = backoff;
+                        backoff = min(backoff * 2, kBypassMax);
+                    } else {
+                        backoff = kBypassTiles;
+                    }
+                }
+            }
             since_norm += kDepPerTile;
-            if (since_norm > kMaxDepositsPerNormalize - kDepPerTile - 2 * (F + 2)) {
+            if (since_norm > kMaxDepositsPerNormalize - kDepPerTile - 2 * kM * (F + 2)) {
                 normalize_column(col, stride);
                 since_norm = 0;
             }
@@ -253,10 +354,17 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
         int since_norm = 0;
         for (long long k = (long long)blockIdx.x * T + tid; k < nscalar; k += gthreads) {
             const long long idx = k < prm.head ? k : k + body;
-            if (DOT) add_product<F, EE, false>(col, stride, a, status, prm.a[idx * prm.inca], prm.b[idx * prm.incb]);
-            else add_value<F, EE, false>(col, stride, a, status, prm.a[idx * prm.inca]);
+            double x[4] = {prm.a[idx * prm.inca], 0.0, 0.0, 0.0};
+            if (DOT) {
+                const double y[4] = {prm.b[idx * prm.incb], 0.0, 0.0, 0.0};
+                mul_add4<F, EE, false>(col, stride, a, status, x, y);
+            } else if (F == 0) {
+                deposit(col, stride, x[0], status);
+            } else {
+                add4<F, EE, false>(col, stride, a, status, x);
+            }
             since_norm += kDepPerElem;
-            if (since_norm > kMaxDepositsPerNormalize - kDepPerElem - 2 * (F + 2)) {
+            if (since_norm > kMaxDepositsPerNormalize - kDepPerElem - 2 * kM * (F + 2)) {
                 normalize_column(col, stride);
                 since_norm = 0;
             }
@@ -264,7 +372,9 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
     }
     if (F > 0) {
 #pragma unroll
-        for (int i = 0; i < F; ++i) deposit(col, stride, a[i], status);
+        for (int i = 0; i < F; ++i)
+#pragma unroll
+            for (int m = 0; m < kM; ++m) deposit(col, stride, a[i][m], status);
     }
     normalize_column(col, stride);
     if (status) atomicOr(&prm.ws->status, status);
@@ -280,9 +390,9 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
         __syncthreads();
         if (tid == 0) normalize(block_limbs);
         __syncthreads();
-        if (tid < (unsigned)kLimbs) {
-            const long long v = block_limbs[tid];
-            if (v != 0) atomicAdd(&prm.ws->gacc[tid], (unsigned long long)v);
+        for (unsigned j = tid; j < (unsigned)kLimbs; j += T) {
+            const long long v = block_limbs[j];
+            if (v != 0) atomicAdd(&prm.ws->gacc[j], (unsigned long long)v);
         }
         __threadfence();
         __syncthreads();
@@ -296,8 +406,8 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
     // ---------------- last CTA: normalise the global accumulator, publish ----------------------
     if (is_last) {
         __threadfence();
-        if (tid < (unsigned)kLimbs)
-            block_limbs[tid] = (long long)atomicExch(&prm.ws->gacc[tid], 0ull);
+        for (unsigned j = tid; j < (unsigned)kLimbs; j += T)
+            block_limbs[j] = (long long)atomicExch(&prm.ws->gacc[j], 0ull);
         __syncthreads();
         if (tid == 0) {
             unsigned st = prm.finalize && !prm.keep ? atomicExch(&prm.ws->status, 0u) : atomicOr(&prm.ws->status, 0u);
@@ -318,8 +428,8 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
         }
         __syncthreads();
         // leave the (normalised) partial sum in the workspace unless this call closes the reduction
-        if ((!prm.finalize || prm.keep) && tid < (unsigned)kLimbs)
-            prm.ws->gacc[tid] = (unsigned long long)block_limbs[tid];
+        if (!prm.finalize || prm.keep)
+            for (unsigned j = tid; j < (unsigned)kLimbs; j += T) prm.ws->gacc[j] = (unsigned long long)block_limbs[j];
     }
 }
 

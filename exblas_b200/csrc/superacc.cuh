@@ -248,17 +248,19 @@ EXB_D void deposit_fast(unsigned col, unsigned stride, unsigned lo, unsigned hi)
     const unsigned m = (unsigned)((int)hi >> 31);                 // all ones when x < 0
     const unsigned long long tm = (unsigned long long)__double_as_longlong(t) ^ (((unsigned long long)m << 32) | m);
     // +D1 = bits(t) - K, -D1 = ~bits(t) + K + 1 with K = bits(2^52) = 0x4330000000000000
-    const unsigned long long ksel = ((unsigned long long)(m ? 0x43300000u : 0xBCD00000u) << 32) | (m & 1u);
+    const unsigned long long ksel = ((unsigned long long)(0xBCD00000u ^ (m & 0xFFE00000u)) << 32) | (0u - m);
     const unsigned a1 = col + J1 * stride;
-    const unsigned a0 = a1 - stride;
+    const unsigned a0 = (col - stride) + J1 * stride;
     const unsigned long long v0 = lds64(a0), v1 = lds64(a1);       // distinct limbs: both loads first
     sts64(a0, v0 + d0);
     sts64(a1, v1 + tm + ksel);
 }
 
-EXB_D bool in_fast_range(unsigned hi) {
-    return (((hi & 0x7fffffffu) >> 20) - kEMin) < (kELim - kEMin);
-}
+// distance of |x| above the lower edge of the fast range, as an unsigned 32-bit key on the high
+// word (so that one unsigned compare tests both edges, and a max over several keys tests them all)
+EXB_D unsigned range_key(unsigned hi) { return (hi & 0x7fffffffu) - (kEMin << 20); }
+constexpr unsigned kRangeSpan = (kELim - kEMin) << 20;
+EXB_D bool in_fast_range(unsigned hi) { return range_key(hi) < kRangeSpan; }
 
 // Slow path for everything else: zeros, specials, values outside the layout, and tiny values
 // (E < 35) whose set bits may still all lie at or above 2^-1040.  Returns status flags.
@@ -281,18 +283,25 @@ __device__ __noinline__ unsigned deposit_slow(unsigned col, unsigned stride, uns
     return st;
 }
 
-// Checked deposit of one double (any value).
+// Checked deposit of one double (any value).  Out of line on purpose: it serves the rare paths
+// (expansion residuals, tails, mixed vectors) and keeping it a call keeps the hot loops small
+// enough for the instruction cache.
+__device__ __noinline__ unsigned deposit_any(unsigned col, unsigned stride, unsigned lo, unsigned hi) {
+    if (in_fast_range(hi)) {
+        deposit_fast(col, stride, lo, hi);
+        return 0u;
+    }
+    return deposit_slow(col, stride, lo, hi);
+}
 EXB_D void deposit(unsigned col, unsigned stride, double x, unsigned& status) {
-    const unsigned lo = (unsigned)__double2loint(x), hi = (unsigned)__double2hiint(x);
-    if (in_fast_range(hi)) deposit_fast(col, stride, lo, hi);
-    else status |= deposit_slow(col, stride, lo, hi);
+    status |= deposit_any(col, stride, (unsigned)__double2loint(x), (unsigned)__double2hiint(x));
 }
 
 // Four independent doubles; one range test for all of them (the common case is all-fast).
 EXB_D void deposit4(unsigned col, unsigned stride, double x0, double x1, double x2, double x3, unsigned& status) {
     const unsigned h0 = (unsigned)__double2hiint(x0), h1 = (unsigned)__double2hiint(x1);
     const unsigned h2 = (unsigned)__double2hiint(x2), h3 = (unsigned)__double2hiint(x3);
-    if (in_fast_range(h0) & in_fast_range(h1) & in_fast_range(h2) & in_fast_range(h3)) {
+    if (max(max(range_key(h0), range_key(h1)), max(range_key(h2), range_key(h3))) < kRangeSpan) {
         deposit_fast(col, stride, (unsigned)__double2loint(x0), h0);
         deposit_fast(col, stride, (unsigned)__double2loint(x1), h1);
         deposit_fast(col, stride, (unsigned)__double2loint(x2), h2);

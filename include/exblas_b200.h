@@ -61,11 +61,14 @@ typedef struct exblas_b200_handle_s* exblas_b200_handle_t;
 int exblas_b200_create(exblas_b200_handle_t* handle, int device);
 int exblas_b200_destroy(exblas_b200_handle_t handle);
 
-/* Use `stream` (a cudaStream_t) for all subsequent work of this handle; NULL = handle's own stream. */
+/* Use `stream` (a cudaStream_t) for all subsequent work of this handle.  A new handle uses the
+ * legacy default stream (NULL), like cuBLAS: ordered after prior default-stream work of the process. */
 int exblas_b200_set_stream(exblas_b200_handle_t handle, void* stream);
 
 /* Tuning knobs (performance only, never the result): "block_threads" (multiple of 32, <= 512),
- * "blocks" (0 = one per SM), "host_chunk_elems". */
+ * "blocks" (0 = one per SM), "host_chunk_elems", "adaptive" (1 = a warp bypasses the expansion and
+ * deposits straight into its superaccumulators while the expansion overflows on most elements;
+ * 0 = always walk all fpe levels, as the reference kernels do). */
 int exblas_b200_set_option(exblas_b200_handle_t handle, const char* name, int64_t value);
 
 /* ---- synchronous entry points: the ones a reference binding calls --------------------------- */

@@ -64,8 +64,8 @@ for kind in ["naive", "logu", "ill"]:
     a = gen(kind, n)
     d = torch.from_numpy(a).to(dev)
     del a
-    for T in [256, 512]:
-        h.set_option("block_threads", T)
+    for T, AD in [(512, 1), (512, 0)]:
+        h.set_option("block_threads", T); h.set_option("adaptive", AD)
         for fpe, ee in [(0, 0), (2, 0), (3, 0), (4, 0), (8, 0), (4, 1), (8, 1)]:
             for _ in range(2): h.exsum_async(n, d, 1, 0, fpe, bool(ee))
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -77,10 +77,10 @@ for kind in ["naive", "logu", "ill"]:
             v, _, st = h.fetch()
             gbs = n * 8 / ms / 1e6
             res.append((kind, T, fpe, ee, ms, gbs))
-            print(f"exsum {kind:6s} T={T} fpe={fpe} ee={ee}: {ms:8.3f} ms  {gbs:8.1f} GB/s  v={v!r} st={st}", flush=True)
+            print(f"exsum {kind:6s} T={T} ad={AD} fpe={fpe} ee={ee}: {ms:8.3f} ms  {gbs:8.1f} GB/s  v={v!r} st={st}", flush=True)
     if kind != "naive":
         b = torch.from_numpy(gen(kind, n)).to(dev)
-        h.set_option("block_threads", 512)
+        h.set_option("block_threads", 512); h.set_option("adaptive", 1)
         for fpe, ee in [(0, 0), (3, 0), (4, 0), (8, 0), (4, 1), (8, 1)]:
             for _ in range(2): h.exdot_async(n, d, 1, 0, b, 1, 0, fpe, bool(ee))
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

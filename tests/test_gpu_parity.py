@@ -249,8 +249,14 @@ def test_specials_and_domain(gpu, oracle):
 def test_argument_errors(gpu):
     import exblas_b200 as xb
     a = np.ones(16)
-    with pytest.raises(xb.ExblasB200Error):
-        gpu.exsum(16, a, 0, 0, 4)                            # inc < 1 -> EINVAL at the C ABI
+    with pytest.raises(ValueError):
+        gpu.exsum(16, a, 0, 0, 4)                            # inc < 1: rejected by the host mirror ...
+    import ctypes as C
+    res = C.c_double()
+    rc = gpu.lib.exblas_b200_exsum(gpu._h, a.ctypes.data, 16, 0, 0, 4, 0, 0, C.byref(res))
+    assert rc == -1                                          # ... and EINVAL at the C ABI
+    rc = gpu.lib.exblas_b200_exsum(gpu._h, a.ctypes.data, 16, 1, 0, -2, 0, 0, C.byref(res))
+    assert rc == -1                                          # fpe < 0
     with pytest.raises(ValueError):
         gpu.exsum(17, a, 1, 0, 4)                            # reads past the end: caught by the host mirror
     with pytest.raises(xb.ExblasB200Error):
