@@ -37,9 +37,8 @@ constexpr int vectors_in_flight(int f, bool ee, bool dot) {
 #ifdef EXB_USUM
     return dot ? EXB_UDOT : EXB_USUM;
 #else
-    if (dot) return (f <= 4 && !ee) ? 4 : 2;
-    if (ee) return 4;
-    return f <= 2 ? 8 : (f <= 4 ? 6 : 4);
+    if (dot) return f <= 4 ? 4 : 3;
+    return f <= 4 ? 8 : 6;
 #endif
 }
 

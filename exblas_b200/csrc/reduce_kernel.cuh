@@ -72,11 +72,11 @@ EXB_D bool nonzero_bits(double x) {
 }
 
 // ---- per-thread state --------------------------------------------------------------------------
-// (col, stride) of the private accumulator column, status flags, and kM independent expansions
-// a[level][m] in registers.  Two expansions per thread give the FP64 pipe independent TwoSum
-// chains to overlap (elements 0,2 of a vector feed expansion 0, elements 1,3 expansion 1); the
-// exact sum does not care how summands are distributed over expansions.
-constexpr int kM = 2;
+// (col, stride) of the private accumulator column, status flags, and M independent expansions
+// a[level][m] in registers.  Two expansions per thread (F <= 4) give the FP64 pipe independent
+// TwoSum chains to overlap (elements 0,2 of a vector feed expansion 0, elements 1,3 expansion 1);
+// the exact sum does not care how summands are distributed over expansions.
+__host__ __device__ constexpr int expansions(int f) { return f <= 4 ? 2 : 1; }   // large F: registers go to the load window instead
 
 // Knuth TwoSum, un-contracted (ExSUM.FPE.cl:27-32): a + x = r + s exactly; a <- r, x <- s.
 EXB_D void two_sum(double& a, double& x) {
@@ -92,14 +92,15 @@ EXB_D void two_sum(double& a, double& x) {
 // this thread (!UNIFORM) holds a non-zero residual: one vote per level per four elements, taken
 // on the integer bit patterns (no FP64-pipe compare, no divergence).  Residuals come back in x[].
 template <int F, bool EE, bool UNIFORM>
-EXB_D void fpe_push4(double (&a)[F > 0 ? F : 1][kM], double (&x)[4], int first) {
+EXB_D void fpe_push4(double (&a)[F > 0 ? F : 1][expansions(F)], double (&x)[4], int first) {
+    constexpr int M1 = expansions(F) - 1;
 #pragma unroll
     for (int i = 0; i < F; ++i) {
         if (i < first) continue;
         two_sum(a[i][0], x[0]);
-        two_sum(a[i][1], x[1]);
+        two_sum(a[i][M1], x[1]);
         two_sum(a[i][0], x[2]);
-        two_sum(a[i][1], x[3]);
+        two_sum(a[i][M1], x[3]);
         if (EE && i + 1 < F) {
             const unsigned any = ((unsigned)__double2hiint(x[0]) | (unsigned)__double2hiint(x[1]) |
                                   (unsigned)__double2hiint(x[2]) | (unsigned)__double2hiint(x[3])) << 1 |
@@ -130,7 +131,7 @@ EXB_D int deposit_residuals(unsigned col, unsigned stride, const double (&x)[4],
 // Four ordinary inputs (any doubles) through the expansion.  No lane leaves early (the votes in
 // fpe_push4 must be reached by all lanes): Inf / NaN / |x| >= 2^988 are diverted and replaced by 0.
 template <int F, bool EE, bool UNIFORM>
-EXB_D int add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][kM], unsigned& status, double (&x)[4]) {
+EXB_D int add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][expansions(F)], unsigned& status, double (&x)[4]) {
     const unsigned h0 = (unsigned)__double2hiint(x[0]) & 0x7fffffffu, h1 = (unsigned)__double2hiint(x[1]) & 0x7fffffffu;
     const unsigned h2 = (unsigned)__double2hiint(x[2]) & 0x7fffffffu, h3 = (unsigned)__double2hiint(x[3]) & 0x7fffffffu;
     if (max(max(h0, h1), max(h2, h3)) >= (kELim << 20)) {
@@ -196,7 +197,7 @@ __device__ __noinline__ unsigned product_slow(unsigned col, unsigned stride, dou
 // through the lower levels (ExDOT.FPE.cl:254-258: level F-3; ExDOT.FPE.EX.4.cl: level 1 with early
 // exit).  F == 0: both parts are deposited directly (ExDOT.Superacc.cl:244-253).
 template <int F, bool EE, bool UNIFORM>
-EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][kM], unsigned& status,
+EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][expansions(F)], unsigned& status,
                    const double (&x)[4], const double (&y)[4]) {
     double p[4], e[4];
     unsigned worst = 0u;
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
     // columns are thread-private: no barrier needed before use
 
     unsigned status = 0;
+    constexpr int kM = expansions(F);
     double a[F > 0 ? F : 1][kM];
 #pragma unroll
     for (int i = 0; i < (F > 0 ? F : 1); ++i)
@@ -299,26 +301,39 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
             const bool has_next = it + 1 < iters;
             const bool direct = (F == 0) || (prm.adaptive && bypass > 0);
             int deposits = 0;
+            // Two separately unrolled tile bodies (only one is hot at a time, so each fits the
+            // instruction cache): direct deposits, or the expansion walk.  Each vector slot is
+            // refilled for the next tile right after it is consumed.
+            if (direct) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
-                double y[4];
-                if (DOT) { y[0] = vb[u].x; y[1] = vb[u].y; y[2] = vb[u].z; y[3] = vb[u].w; }
-                if (direct) {
+                for (int u = 0; u < U; ++u) {
                     if (DOT) {
-                        double none[1][kM];
+                        const double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                        const double y[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+                        double none[1][expansions(0)];
                         mul_add4<0, false, true>(col, stride, none, status, x, y);
                     } else {
-                        deposit4(col, stride, x[0], x[1], x[2], x[3], status);
+                        deposit4(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
                     }
-                } else {
-                    if (DOT) deposits += mul_add4<F, EE, true>(col, stride, a, status, x, y);
-                    else deposits += add4<F, EE, true>(col, stride, a, status, x);
+                    if (has_next) {
+                        va[u] = ldg256(pa + u * vstep);
+                        if (DOT) vb[u] = ldg256(pb + u * vstep);
+                    }
                 }
-                // refill this slot for the next tile (consumed one full iteration from now)
-                if (has_next) {
-                    va[u] = ldg256(pa + u * vstep);
-                    if (DOT) vb[u] = ldg256(pb + u * vstep);
+            } else if (F > 0) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                    if (DOT) {
+                        const double y[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+                        deposits += mul_add4<F, EE, true>(col, stride, a, status, x, y);
+                    } else {
+                        deposits += add4<F, EE, true>(col, stride, a, status, x);
+                    }
+                    if (has_next) {
+                        va[u] = ldg256(pa + u * vstep);
+                        if (DOT) vb[u] = ldg256(pb + u * vstep);
+                    }
                 }
             }
             if (F > 0 && prm.adaptive) {
