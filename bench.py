@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--op", default="exsum", choices=["exsum", "exdot"])
@@ -155,13 +155,13 @@ def cpu_run(args, fpes, log2n, reps):
     ee = bool(args.early_exit)
     if args.op == "exsum" and Reference.available():
         ref = Reference()
-        kind, cores = "reference", ref.max_threads()
+        kind, cores = "reference", ref.use_all_cores()
 
         def one(fpe):
             return ref.exsum(a, fpe=fpe, early_exit=ee, parallel=True)
     else:
         O = Oracle()
-        kind, cores = "port", (O.max_threads() if args.op == "exsum" else 1)
+        kind, cores = "port", (O.use_all_cores() if args.op == "exsum" else 1)
 
         def one(fpe):
             if args.op == "exsum":

@@ -353,6 +353,7 @@ void oracle_init_naive(int64_t n, double* a) {
 #ifdef _OPENMP
 #include <omp.h>
 int oracle_max_threads(void) { return omp_get_max_threads(); }
+void oracle_set_threads(int n) { omp_set_num_threads(n); }
 double oracle_exsum_parallel(int64_t n, const double* a, int fpe, int early_exit, int round_mode) {
     int T = omp_get_max_threads();
     ob_acc* accs = (ob_acc*)malloc(sizeof(ob_acc) * (size_t)T);
@@ -379,6 +380,7 @@ double oracle_exsum_parallel(int64_t n, const double* a, int fpe, int early_exit
 }
 #else
 int oracle_max_threads(void) { return 1; }
+void oracle_set_threads(int n) { (void)n; }
 double oracle_exsum_parallel(int64_t n, const double* a, int fpe, int early_exit, int round_mode) {
     return oracle_exsum(n, a, 1, 0, fpe, early_exit, round_mode, 0);
 }

@@ -62,6 +62,7 @@ class Oracle:
         L.oracle_exsum_parallel.restype = C.c_double
         L.oracle_exsum_parallel.argtypes = [C.c_int64, _dp, C.c_int, C.c_int, C.c_int]
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_set_threads.argtypes = [C.c_int]
         self.L = L
 
     def exsum(self, a, inca=1, offset=0, fpe=0, early_exit=False, round_mode=0, n=None):
@@ -109,6 +110,11 @@ class Oracle:
     def max_threads(self) -> int:
         return int(self.L.oracle_max_threads())
 
+    def use_all_cores(self) -> int:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.L.oracle_set_threads(n)
+        return self.max_threads()
+
 
 class Reference:
     """The unmodified reference CPU library (41-limb CPU layout)."""
@@ -134,6 +140,7 @@ class Reference:
         L.ref_exdot_mpfr.restype = C.c_double
         L.ref_exdot_mpfr.argtypes = [C.c_long, _dp, _dp]
         L.ref_omp_max_threads.restype = C.c_int
+        L.ref_omp_set_threads.argtypes = [C.c_int]
         L.ref_limb_count.restype = C.c_int
         L.ref_f_words.restype = C.c_int
         L.ref_srand.argtypes = [C.c_uint]
@@ -176,6 +183,12 @@ class Reference:
 
     def max_threads(self) -> int:
         return int(self.L.ref_omp_max_threads())
+
+    def use_all_cores(self) -> int:
+        """torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use every host core."""
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.L.ref_omp_set_threads(n)
+        return self.max_threads()
 
     def init_naive(self, n):
         a = np.empty(n, dtype=np.float64)

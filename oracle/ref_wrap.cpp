@@ -53,6 +53,7 @@ void mpfr_free_cache(void);
 extern "C" {
 
 int ref_omp_max_threads(void) { return omp_get_max_threads(); }
+void ref_omp_set_threads(int n) { omp_set_num_threads(n); }
 
 int ref_limb_count(void) {
     Superaccumulator s(e_bits, f_bits);

@@ -63,7 +63,7 @@ def test_sharded_equals_single_gpu(gpu):
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
         pytest.skip("needs >= 2 GPUs")
-    n = 10_000_001
+    n = 10_000_002
     for world in sorted({2, min(ngpu, 4), min(ngpu, 8)}):
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
@@ -71,7 +71,18 @@ def test_sharded_equals_single_gpu(gpu):
         procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
         for p in procs:
             p.start()
-        results = dict(q.get(timeout=300) for _ in range(world))
+        results = {}
+        import queue as _q
+        import time as _t
+        t0 = _t.time()
+        while len(results) < world:
+            try:
+                r, out = q.get(timeout=5)
+                results[r] = out
+            except _q.Empty:
+                dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+                assert not dead, f"a rank died with exit code {dead}"
+                assert _t.time() - t0 < 600, "timeout waiting for ranks"
         for p in procs:
             p.join(timeout=120)
             assert p.exitcode == 0
