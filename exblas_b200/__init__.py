@@ -5,11 +5,12 @@ Python host layer that mirrors the reference's blas1.hpp interface.  No CPU fall
 """
 from ._lib import (LIMBS, ROUND_EXACT, ROUND_REFERENCE, ST_NAN, ST_NEGINF, ST_POSINF, ST_TOOLARGE, ST_TOOSMALL,
                    ExblasB200Error)
+from .blas2 import exgemv
 from .blas1 import (Handle, default_handle, exdot, exsum, merge_limbs, nccl_unique_id, normalize_limbs,
                     round_limbs)
 
 __all__ = [
     "LIMBS", "ROUND_EXACT", "ROUND_REFERENCE", "ST_NAN", "ST_NEGINF", "ST_POSINF", "ST_TOOLARGE", "ST_TOOSMALL",
-    "ExblasB200Error", "Handle", "default_handle", "exdot", "exsum", "merge_limbs", "nccl_unique_id",
+    "ExblasB200Error", "Handle", "default_handle", "exdot", "exgemv", "exsum", "merge_limbs", "nccl_unique_id",
     "normalize_limbs", "round_limbs",
 ]

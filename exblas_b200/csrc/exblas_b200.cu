@@ -21,6 +21,7 @@
 
 #include "../../include/exblas_b200.h"
 #include "reduce_kernel.cuh"
+#include "gemv_kernel.cuh"
 
 using namespace exb;
 
@@ -98,10 +99,13 @@ struct exblas_b200_handle_s {
     Result* h_res = nullptr;                // pinned
     double* d_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][a|b]
     int64_t stage_elems = 0;
+    long long* d_gemv_scratch = nullptr;    // [parts][39][m] limbs + [parts][m] status words
+    size_t gemv_scratch_bytes = 0;
     int64_t opt_block_threads = kMaxT;
     int64_t opt_blocks = 0;
     int64_t opt_host_chunk = (int64_t)1 << 23;
     int64_t opt_adaptive = 1;
+    int64_t opt_gemv_parts = 0;
     void* comm = nullptr;
     int nranks = 1;
     int64_t launches = 0;
@@ -311,6 +315,103 @@ int fetch_result(exblas_b200_handle_t h, double* result, int64_t* limbs, uint32_
     return EXBLAS_B200_OK;
 }
 
+typedef void (*gemv_fn)(const GemvParams);
+
+constexpr int gemv_groups_in_flight(int f) { return f <= 4 ? 4 : 2; }
+
+template <int F, bool EE>
+gemv_fn gemv_ptr() {
+    return exgemv_n_kernel<F, EE, gemv_groups_in_flight(F), kMaxT>;
+}
+
+gemv_fn select_gemv(int f, bool ee) {
+    if (ee) {
+        switch (f) {
+            case 4: return gemv_ptr<4, true>();
+            case 6: return gemv_ptr<6, true>();
+            default: return gemv_ptr<8, true>();
+        }
+    }
+    switch (f) {
+        case 0: return gemv_ptr<0, false>();
+        case 2: return gemv_ptr<2, false>();
+        case 3: return gemv_ptr<3, false>();
+        case 4: return gemv_ptr<4, false>();
+        case 5: return gemv_ptr<5, false>();
+        case 6: return gemv_ptr<6, false>();
+        case 7: return gemv_ptr<7, false>();
+        default: return gemv_ptr<8, false>();
+    }
+}
+
+// Column split: enough CTAs to fill every SM for whole waves, as little limb scratch as possible.
+int choose_gemv_parts(int64_t row_blocks, int64_t n, int num_sms) {
+    int best = 1;
+    double best_cost = 1e300;
+    const int64_t pmax = n / 64 > 0 ? (n / 64 < 64 ? n / 64 : 64) : 1;
+    for (int p = 1; p <= pmax; ++p) {
+        const double ctas = (double)row_blocks * p;
+        const double waves = ceil(ctas / num_sms);
+        const double eff = ctas / (waves * num_sms);
+        const double cost = (1.0 / eff) * (1.0 + 78.0 * p / (double)n) + 1e-9 * p;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = p;
+        }
+    }
+    return best;
+}
+
+int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, const double* a, int64_t lda,
+                const double* x, int64_t incx, double beta, double* y, int64_t incy, int f, bool ee, int round_mode) {
+    int T = (int)h->opt_block_threads;
+    if (m < T) T = (int)((m + 31) / 32 * 32);
+    if (T < 32) T = 32;
+    const int64_t row_blocks = (m + T - 1) / T;
+    int parts = h->opt_gemv_parts > 0 ? (int)h->opt_gemv_parts : choose_gemv_parts(row_blocks, n, h->num_sms);
+    int64_t cpp = ((n + parts - 1) / parts + 3) / 4 * 4;
+    if (cpp < 4) cpp = 4;
+    parts = (int)((n + cpp - 1) / cpp);
+    if (parts < 1) parts = 1;
+    const size_t need = (size_t)parts * m * (kLimbs * sizeof(long long) + sizeof(unsigned));
+    if (need > h->gemv_scratch_bytes) {
+        if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
+        h->d_gemv_scratch = nullptr;
+        h->gemv_scratch_bytes = 0;
+        CK(cudaMalloc(&h->d_gemv_scratch, need));
+        h->gemv_scratch_bytes = need;
+    }
+    GemvParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = a;
+    p.x = x;
+    p.y = y;
+    p.m = m;
+    p.n = n;
+    p.lda = lda;
+    p.incx = incx;
+    p.incy = incy;
+    p.alpha = alpha;
+    p.beta = beta;
+    p.cols_per_part = cpp;
+    p.parts = parts;
+    p.scratch = h->d_gemv_scratch;
+    p.row_status = (unsigned*)(h->d_gemv_scratch + (size_t)parts * kLimbs * m);
+    p.ws = h->d_ws;
+    p.round_mode = round_mode;
+    p.adaptive = h->opt_adaptive ? 1 : 0;
+    gemv_fn fn = select_gemv(f, ee);
+    const size_t smem = (size_t)T * kLimbs * sizeof(long long);
+    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {(void*)&p};
+    CK(cudaLaunchKernel((const void*)fn, dim3((unsigned)row_blocks, (unsigned)parts), dim3((unsigned)T), args, smem,
+                        h->stream));
+    exgemv_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(p);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return EXBLAS_B200_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -383,6 +484,7 @@ int exblas_b200_destroy(exblas_b200_handle_t h) {
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j)
             if (h->d_stage[i][j]) cudaFree(h->d_stage[i][j]);
+    if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_res) cudaFree(h->d_res);
     if (h->h_res) cudaFreeHost(h->h_res);
@@ -409,6 +511,9 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "blocks")) {
         if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;    // 2048 partials of < 2^52 fit a limb
         h->opt_blocks = value;
+    } else if (!strcmp(name, "gemv_parts")) {
+        if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;
+        h->opt_gemv_parts = value;
     } else if (!strcmp(name, "adaptive")) {
         h->opt_adaptive = value != 0;
     } else if (!strcmp(name, "host_chunk_elems")) {
@@ -469,6 +574,74 @@ int exblas_b200_exdot(exblas_b200_handle_t h, const double* a, int64_t inca, int
     if (!result) return EXBLAS_B200_EINVAL;
     return exblas_b200_exdot_limbs(h, a, inca, offseta, b, incb, offsetb, n, fpe, early_exit, round_mode, nullptr,
                                    result);
+}
+
+int exblas_b200_exgemv(exblas_b200_handle_t h, char trans, int64_t m, int64_t n, double alpha, const double* a,
+                       int64_t lda, int64_t offseta, const double* x, int64_t incx, int64_t offsetx, double beta,
+                       double* y, int64_t incy, int64_t offsety, int fpe, int early_exit, int round_mode) {
+    if (!h) return EXBLAS_B200_EINVAL;
+    if (trans != 'N' && trans != 'n') {
+        h->err = "exgemv: only the non-transpose case ('N') is implemented";
+        return EXBLAS_B200_EINVAL;
+    }
+    if (m < 0 || n < 0 || lda < (m > 1 ? m : 1) || incx < 1 || incy < 1 || fpe < 0 || offseta < 0 || offsetx < 0 ||
+        offsety < 0 || (m > 0 && (!y || (n > 0 && (!a || !x))))) {
+        h->err = "exgemv: invalid argument";
+        return EXBLAS_B200_EINVAL;
+    }
+    if (m == 0) return EXBLAS_B200_OK;
+    CK(cudaSetDevice(h->device));
+    // fpe: 0 superaccumulators only; 1 is the reference's plain (non-reproducible) DGEMV comparator
+    // (ExGEMV.cpp:92-94) -- here it also runs the exact superaccumulator kernel; early exit buckets 4/6/8.
+    int f = fpe <= 1 ? 0 : (early_exit ? (fpe <= 4 ? 4 : (fpe <= 6 ? 6 : 8)) : (fpe > 8 ? 8 : fpe));
+    const bool ee = early_exit && f > 0;
+    const double* pa = a ? a + offseta : a;
+    const double* px = x ? x + offsetx : x;
+    double* py = y + offsety;
+    const bool dev = is_device_pointer(py) && (n == 0 || (is_device_pointer(pa) && is_device_pointer(px)));
+    int rc;
+    if (dev) {
+        rc = gemv_device(h, m, n, alpha, pa, lda, px, incx, beta, py, incy, f, ee, round_mode);
+        if (rc) return rc;
+    } else {
+        // host operands (what the reference's exgemv takes, ExGEMV.cpp:109-234): stage on the device
+        double *da = nullptr, *dx = nullptr, *dy = nullptr;
+        const size_t na = n > 0 ? (size_t)lda * (n - 1) + m : 0, nx = n > 0 ? (size_t)(n - 1) * incx + 1 : 0,
+                     ny = (size_t)(m - 1) * incy + 1;
+        rc = [&]() -> int {
+            if (na) CK(cudaMalloc(&da, na * sizeof(double)));
+            if (nx) CK(cudaMalloc(&dx, nx * sizeof(double)));
+            CK(cudaMalloc(&dy, ny * sizeof(double)));
+            if (na) CK(cudaMemcpyAsync(da, pa, na * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            if (nx) CK(cudaMemcpyAsync(dx, px, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(dy, py, ny * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            int r2 = gemv_device(h, m, n, alpha, da, lda, dx, incx, beta, dy, incy, f, ee, round_mode);
+            if (r2) return r2;
+            CK(cudaMemcpyAsync(py, dy, ny * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            return EXBLAS_B200_OK;
+        }();
+        if (da) cudaFree(da);
+        if (dx) cudaFree(dx);
+        if (dy) cudaFree(dy);
+        if (rc) return rc;
+    }
+    // status word: read and reset (stream ordered)
+    CK(cudaMemcpyAsync(&h->h_res->status, &h->d_ws->status, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemsetAsync(&h->d_ws->status, 0, sizeof(unsigned), h->stream));
+    if (!dev) {
+        CK(cudaStreamSynchronize(h->stream));
+        h->last_status = h->h_res->status;
+    }
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_sync(exblas_b200_handle_t h) {
+    if (!h) return EXBLAS_B200_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->last_status = h->h_res->status;
+    return EXBLAS_B200_OK;
 }
 
 int exblas_b200_round(const int64_t* limbs, int round_mode, double* result) {
@@ -620,4 +793,18 @@ double exdot(const int Ng, double* ag, const int inca, const int offseta, double
         exit(EXIT_FAILURE);
     }
     return r;
+}
+
+int exgemv(const char transa, const int m, const int n, const double alpha, double* a, const int lda, const int offseta,
+           double* x, const int incx, const int offsetx, const double beta, double* y, const int incy, const int offsety,
+           const int fpe, const bool early_exit) {
+    exblas_b200_handle_t h = default_handle();
+    int rc = exblas_b200_exgemv(h, transa, m, n, alpha, a, lda, offseta, x, incx, offsetx, beta, y, incy, offsety, fpe,
+                                early_exit ? 1 : 0, default_round_mode());
+    if (rc == EXBLAS_B200_OK) rc = exblas_b200_sync(h);
+    if (rc != EXBLAS_B200_OK) {
+        fprintf(stderr, "exgemv: %s (%s)\n", exblas_b200_strerror(rc), exblas_b200_last_error(h));
+        exit(EXIT_FAILURE);      // the reference prints and exits on OpenCL errors (ExGEMV.cpp:120-160)
+    }
+    return 0;
 }

@@ -187,6 +187,50 @@ EXB_HD double round_exact(const long long* acc, bool negative) {
     return negative ? -r : r;
 }
 
+// Exact accumulation of one double into a plain limb array (not the hot path: used where a value
+// is added once per output, e.g. beta*y in ExGEMV, and on the host).  Integer split of the 53-bit
+// mantissa into <= 3 limb digits.  Returns status flags.
+EXB_HD unsigned accumulate_double(long long* acc, double x) {
+    unsigned long long u;
+#if defined(__CUDA_ARCH__)
+    u = (unsigned long long)__double_as_longlong(x);
+#else
+    std::memcpy(&u, &x, 8);
+#endif
+    const unsigned E = (unsigned)((u >> 52) & 0x7ffu);
+    unsigned long long mant = u & ((1ull << 52) - 1ull);
+    const bool neg = (u >> 63) != 0;
+    if (E == 0 && mant == 0) return 0u;
+    if (E == 0x7ffu) return mant ? kStNaN : (neg ? kStNegInf : kStPosInf);
+    if (E >= kELim) return kStTooLarge;
+    unsigned st = 0u;
+    int pos;                                    // position of the mantissa LSB above the accumulator LSB
+    if (E == 0) pos = 1 - 1075 + 1040; else { mant |= 1ull << 52; pos = (int)E - 1075 + 1040; }
+    if (pos < 0) {
+        const int sh = -pos;
+        if (sh >= 64) { return kStTooSmall; }
+        if (mant & ((1ull << sh) - 1ull)) st |= kStTooSmall;
+        mant >>= sh;
+        pos = 0;
+    }
+    const int j = pos / kDigits, s = pos % kDigits;
+    // mant << s spans up to 105 bits: digits for limbs j, j+1, j+2
+    const unsigned long long lo = (mant << s) & (unsigned long long)kLimbMask;
+    const unsigned long long rest = s ? (mant >> (kDigits - s)) : (mant >> kDigits);   // bits above limb j
+    const unsigned long long mid = rest & (unsigned long long)kLimbMask;
+    const unsigned long long hi = rest >> kDigits;
+    if (neg) {
+        acc[j] -= (long long)lo;
+        if (j + 1 < kLimbs) acc[j + 1] -= (long long)mid;
+        if (j + 2 < kLimbs) acc[j + 2] -= (long long)hi;
+    } else {
+        acc[j] += (long long)lo;
+        if (j + 1 < kLimbs) acc[j + 1] += (long long)mid;
+        if (j + 2 < kLimbs) acc[j + 2] += (long long)hi;
+    }
+    return st;
+}
+
 // Final value from limbs + status flags (IEEE semantics for the specials the kernel met).
 EXB_HD double finalize_value(long long* acc, unsigned status, int round_mode) {
     bool neg = normalize(acc);

@@ -66,7 +66,7 @@ int exblas_b200_destroy(exblas_b200_handle_t handle);
 int exblas_b200_set_stream(exblas_b200_handle_t handle, void* stream);
 
 /* Tuning knobs (performance only, never the result): "block_threads" (multiple of 32, <= 512),
- * "blocks" (0 = one per SM), "host_chunk_elems", "adaptive" (1 = a warp bypasses the expansion and
+ * "blocks" (0 = one per SM), "host_chunk_elems", "gemv_parts" (0 = automatic column split), "adaptive" (1 = a warp bypasses the expansion and
  * deposits straight into its superaccumulators while the expansion overflows on most elements;
  * 0 = always walk all fpe levels, as the reference kernels do). */
 int exblas_b200_set_option(exblas_b200_handle_t handle, const char* name, int64_t value);
@@ -105,6 +105,22 @@ int exblas_b200_exdot_async(exblas_b200_handle_t handle, const double* d_a, int6
 int exblas_b200_fetch(exblas_b200_handle_t handle, double* result, int64_t limbs[EXBLAS_B200_LIMBS], uint32_t* status);
 /* Device address of the result slot: { double value; uint32 status; uint32 pad; int64 limbs[39]; } */
 int exblas_b200_result_ptr(exblas_b200_handle_t handle, void** d_result);
+
+/* ---- ExGEMV 'N' (BASELINE config 5) --------------------------------- */
+
+/* replaces exgemv()  (reference include/blas2.hpp:95; src/gpu/blas/blas2/ExGEMV.cpp:81-234) for
+ * transa == 'N': y := alpha*A*x + beta*y, A column-major m x n with leading dimension lda, every
+ * y[i] the rounded EXACT value (per-row ExDOT).  Operands may all be host or all be device
+ * pointers; with device pointers the call is asynchronous on the handle's stream (follow with
+ * exblas_b200_sync to read the status flags).  fpe: 0 / 1 superaccumulators only (the reference's
+ * fpe == 1 is a plain DGEMV comparator), early_exit buckets 4 / 6 / 8, else the expansion size.
+ * Deviation from the reference kernels: alpha is applied (exactly); ExGEMV.FPE.cl:246 ignores it. */
+int exblas_b200_exgemv(exblas_b200_handle_t handle, char trans, int64_t m, int64_t n, double alpha,
+                       const double* a, int64_t lda, int64_t offseta, const double* x, int64_t incx,
+                       int64_t offsetx, double beta, double* y, int64_t incy, int64_t offsety,
+                       int fpe, int early_exit, int round_mode);
+/* Wait for the handle's stream and latch the status flags of the last asynchronous call. */
+int exblas_b200_sync(exblas_b200_handle_t handle);
 
 /* ---- limb arithmetic on the host (no GPU needed) ------------------------------------------- */
 

@@ -309,6 +309,64 @@ double oracle_exdot(int64_t n, const double* a, int64_t inca, int64_t offa, cons
     return round_mode ? ob_round_exact(&s) : ob_round_ref(&s);
 }
 
+/* exgemv: y := alpha*op(A)*x + beta*y, A column-major with leading dimension lda.
+ * Per output element the reference kernel (src/gpu/blas/blas2/ExGEMV.FPE.cl:244-288; 'T':
+ * :420-470) runs TwoProductFMA, feeds both parts through ALL levels of the row's expansion
+ * (first level 0, :272-276), flushes like ExSUM, then adds beta*y exactly (:346-377: beta == 0
+ * nothing, beta == 1 the value, else TwoProductFMA) and rounds.  The reference's non-transpose
+ * FPE kernel ignores alpha (:246) and its tests only use alpha == 1; here alpha is applied exactly
+ * (alpha*a = p1 + e1 by TwoProd, then (p1 + e1)*x by two TwoProds), which coincides with the
+ * reference for alpha == 1.  fpe <= 1 -> superaccumulators only (fpe == 1 is a plain DGEMV in the
+ * reference, ExGEMV.cpp:92-94: not an exact algorithm, not restated). */
+static void ob_gemv_term(ob_acc* s, double* e, int f, int ee, double av, double xv) {
+    double r;
+    double p = ob_two_prod(av, xv, &r);
+    if (f == 0) {
+        ob_accumulate(s, p);
+        if (r != 0.0) ob_accumulate(s, r);
+    } else {
+        ob_fpe_push(s, e, f, ee, 0, p);
+        if (r != 0.0) ob_fpe_push(s, e, f, ee, 0, r);
+    }
+}
+
+int oracle_exgemv(char trans, int64_t m, int64_t n, double alpha, const double* a, int64_t lda, const double* x,
+                  int64_t incx, double beta, double* y, int64_t incy, int fpe, int early_exit, int round_mode) {
+    const int t = (trans == 'T' || trans == 't');
+    const int64_t nout = t ? n : m, nin = t ? m : n;
+    int f = fpe <= 1 ? 0 : ob_fpe_size(fpe, early_exit, 2);
+    for (int64_t i = 0; i < nout; ++i) {
+        ob_acc s;
+        ob_init(&s, 1);
+        double e[8] = {0};
+        for (int64_t j = 0; j < nin; ++j) {
+            const double av = t ? a[i * lda + j] : a[j * lda + i];
+            const double xv = x[j * incx];
+            if (alpha == 1.0) {
+                ob_gemv_term(&s, e, f, early_exit, av, xv);
+            } else {
+                double e1;
+                double p1 = ob_two_prod(alpha, av, &e1);
+                ob_gemv_term(&s, e, f, early_exit, p1, xv);
+                if (e1 != 0.0) ob_gemv_term(&s, e, f, early_exit, e1, xv);
+            }
+        }
+        for (int k = 0; k < f; ++k) ob_accumulate(&s, e[k]);
+        if (beta != 0.0) {
+            if (beta == 1.0) {
+                ob_accumulate(&s, y[i * incy]);
+            } else {
+                double r;
+                double p = ob_two_prod(beta, y[i * incy], &r);
+                ob_accumulate(&s, p);
+                if (r != 0.0) ob_accumulate(&s, r);
+            }
+        }
+        y[i * incy] = round_mode ? ob_round_exact(&s) : ob_round_ref(&s);
+    }
+    return 0;
+}
+
 /* Exact accumulation on a chosen layout, exporting all limbs (for comparison with the reference class). */
 double oracle_superacc_limbs(int64_t n, const double* a, int layout, int64_t* limbs_out, int round_mode) {
     ob_acc s;

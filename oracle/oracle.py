@@ -61,6 +61,9 @@ class Oracle:
         L.oracle_merge_round.argtypes = [_lp, C.c_int, C.c_int, C.c_int, _lp]
         L.oracle_exsum_parallel.restype = C.c_double
         L.oracle_exsum_parallel.argtypes = [C.c_int64, _dp, C.c_int, C.c_int, C.c_int]
+        L.oracle_exgemv.restype = C.c_int
+        L.oracle_exgemv.argtypes = [C.c_char, C.c_int64, C.c_int64, C.c_double, _dp, C.c_int64, _dp, C.c_int64,
+                                    C.c_double, _dp, C.c_int64, C.c_int, C.c_int, C.c_int]
         L.oracle_max_threads.restype = C.c_int
         L.oracle_set_threads.argtypes = [C.c_int]
         self.L = L
@@ -103,6 +106,15 @@ class Oracle:
                                       out.ctypes.data_as(_lp))
         return r, out
 
+    def exgemv(self, trans, m, n, alpha, a, lda, x, incx, beta, y, incy, fpe=0, early_exit=False, round_mode=0):
+        """returns the new y (input y is not modified)"""
+        a = _as_f64(a)
+        x = _as_f64(x)
+        out = np.array(y, dtype=np.float64, copy=True)
+        self.L.oracle_exgemv(trans.encode(), m, n, alpha, _ptr(a), lda, _ptr(x), incx, beta, _ptr(out), incy, fpe,
+                             int(early_exit), round_mode)
+        return out
+
     def exsum_parallel(self, a, fpe=8, early_exit=True, round_mode=0):
         a = _as_f64(a)
         return self.L.oracle_exsum_parallel(a.size, _ptr(a), fpe, int(early_exit), round_mode)
@@ -139,6 +151,8 @@ class Reference:
         L.ref_exsum_mpfr.argtypes = [C.c_long, _dp]
         L.ref_exdot_mpfr.restype = C.c_double
         L.ref_exdot_mpfr.argtypes = [C.c_long, _dp, _dp]
+        L.ref_exgemv_mpfr.argtypes = [C.c_char, C.c_int, C.c_int, C.c_double, _dp, C.c_int, _dp, C.c_int, C.c_double,
+                                      _dp, C.c_int, _dp]
         L.ref_omp_max_threads.restype = C.c_int
         L.ref_omp_set_threads.argtypes = [C.c_int]
         L.ref_limb_count.restype = C.c_int
@@ -171,6 +185,15 @@ class Reference:
         limbs = np.zeros(41, dtype=np.int64)
         r = self.L.ref_exdot_superacc(a.size, _ptr(a), _ptr(b), limbs.ctypes.data_as(_lp))
         return r, limbs
+
+    def exgemv_mpfr(self, trans, m, n, alpha, a, lda, x, incx, beta, y, incy):
+        a = _as_f64(a)
+        x = _as_f64(x)
+        y = _as_f64(y)
+        nout = n if trans == "T" else m
+        out = np.zeros(nout, dtype=np.float64)
+        self.L.ref_exgemv_mpfr(trans.encode(), m, n, alpha, _ptr(a), lda, _ptr(x), incx, beta, _ptr(y), incy, _ptr(out))
+        return out
 
     def exsum_mpfr(self, a):
         a = _as_f64(a)

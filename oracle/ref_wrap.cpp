@@ -133,6 +133,34 @@ double ref_exdot_mpfr(long n, const double* a, const double* b) {
     return d;
 }
 
+// tests/test.exgemv.gpu.cpp:35-78 exgemvVsMPFR (column-major), returning the per-element MPFR
+// values instead of the norm: dot = a (128 bit) * alpha * x, sum (2098 bit) += dot, + beta*y.
+// Exact (hence correctly rounded) whenever alpha == 1 (a*x needs 106 <= 128 bits).
+void ref_exgemv_mpfr(char trans, int m, int n, double alpha, const double* a, int lda, const double* x, int incx,
+                     double beta, const double* y, int incy, double* out) {
+    ob_mpfr_t sum, dot;
+    mpfr_init2(dot, 128);
+    mpfr_init2(sum, 2098);
+    const bool t = (trans == 'T');
+    const int nout = t ? n : m, nin = t ? m : n;
+    for (int i = 0; i < nout; ++i) {
+        mpfr_set_d(sum, 0.0, OB_MPFR_RNDN);
+        for (int j = 0; j < nin; ++j) {
+            mpfr_set_d(dot, t ? a[i * lda + j] : a[j * lda + i], OB_MPFR_RNDN);
+            mpfr_mul_d(dot, dot, alpha, OB_MPFR_RNDN);
+            mpfr_mul_d(dot, dot, x[j * incx], OB_MPFR_RNDN);
+            mpfr_add(sum, sum, dot, OB_MPFR_RNDN);
+        }
+        mpfr_set_d(dot, y[i * incy], OB_MPFR_RNDN);
+        mpfr_mul_d(dot, dot, beta, OB_MPFR_RNDN);
+        mpfr_add(sum, sum, dot, OB_MPFR_RNDN);
+        out[i] = mpfr_get_d(sum, OB_MPFR_RNDN);
+    }
+    mpfr_clear(dot);
+    mpfr_clear(sum);
+    mpfr_free_cache();
+}
+
 void ref_srand(unsigned seed) { srand(seed); }
 void ref_init_naive(int n, double* a) { init_naive(n, a); }
 void ref_init_fpuniform(int n, double* a, int range, int emax) { init_fpuniform(n, a, range, emax); }

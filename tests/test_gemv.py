@@ -1,0 +1,137 @@
+"""ExGEMV 'N' (BASELINE config 5).
+
+CPU: the oracle's exgemv against exact rationals and against the reference tests' MPFR checker
+(tests/test.exgemv.gpu.cpp:35-78, compiled into oracle/_ref).  GPU: the CUDA path through the C ABI
+against the oracle, bit for bit, including alpha / beta / lda / inc / offsets / column splits."""
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from exblas_b200 import common as cm
+
+VARIANTS = [(0, False), (1, False), (2, False), (3, False), (4, False), (8, False), (4, True), (6, True), (8, True)]
+
+
+def make(m, n, lda, kind, seed):
+    a = np.zeros(lda * n)
+    if kind == "loguniform":
+        A = cm.init_fpuniform(m * n, 300, 150, seed=seed, neg_ratio=2)
+        x = cm.init_fpuniform(n, 300, 150, seed=seed + 1, neg_ratio=3)
+    elif kind == "illcond":
+        A = cm.init_ill_cond(max(m * n, 2), 1e32, seed=seed)[: m * n]
+        x = cm.init_ill_cond(max(n, 2), 1e32, seed=seed + 1)[:n]
+    else:
+        A = np.full(m * n, 1.1)
+        x = np.full(n, 1.1)
+    a.reshape(n, lda)[:, :m] = A.reshape(n, m)
+    y = cm.init_fpuniform(m, 100, 50, seed=seed + 2, neg_ratio=2)
+    return a, x, y
+
+
+def exact(m, n, alpha, a, lda, x, beta, y):
+    A = a.reshape(n, lda)
+    return np.array([float(sum(Fraction(alpha) * Fraction(float(A[j, i])) * Fraction(float(x[j])) for j in range(n))
+                           + Fraction(beta) * Fraction(float(y[i]))) for i in range(m)])
+
+
+def test_oracle_exgemv_exact_and_mpfr(oracle):
+    for (m, n, lda) in [(1, 1, 1), (5, 7, 5), (40, 33, 43), (64, 64, 64)]:
+        for kind in ("loguniform", "illcond", "naive"):
+            a, x, y = make(m, n, lda, kind, seed=m + n)
+            for alpha, beta in [(1.0, 1.0), (1.0, 0.0), (1.0, -2.5), (3.7, 0.3)]:
+                want = exact(m, n, alpha, a, lda, x, beta, y)
+                for fpe, ee in VARIANTS:
+                    got = oracle.exgemv("N", m, n, alpha, a, lda, x, 1, beta, y, 1, fpe, ee, 1)
+                    assert (got == want).all(), (m, n, kind, alpha, beta, fpe, ee)
+                # reference-compatible rounding differs from exact only through Round()'s known defect
+                g0 = oracle.exgemv("N", m, n, alpha, a, lda, x, 1, beta, y, 1, 4, False, 0)
+                assert np.allclose(g0, want, rtol=4e-16, atol=0)
+
+
+def test_oracle_exgemv_vs_reference_mpfr_checker(oracle, reference):
+    for (m, n, lda) in [(40, 33, 43), (64, 100, 64)]:
+        a, x, y = make(m, n, lda, "loguniform", seed=7)
+        for beta in (1.0, 0.0, 0.5):
+            mp = reference.exgemv_mpfr("N", m, n, 1.0, a, lda, x, 1, beta, y, 1)
+            got = oracle.exgemv("N", m, n, 1.0, a, lda, x, 1, beta, y, 1, 8, True, 1)
+            assert (got == mp).all()
+
+
+@pytest.mark.gpu
+def test_exgemv_gpu_vs_oracle(gpu, oracle):
+    import torch
+    import exblas_b200 as xb
+    shapes = [(1, 1, 1), (5, 7, 5), (33, 100, 40), (512, 64, 512), (513, 1030, 520), (1500, 257, 1500), (100, 5000, 128)]
+    for (m, n, lda) in shapes:
+        for kind in ("loguniform", "illcond", "naive"):
+            a, x, y = make(m, n, lda, kind, seed=m * 3 + n)
+            for alpha, beta in [(1.0, 1.0), (1.0, 0.0), (-0.75, 2.5)]:
+                w0 = oracle.exgemv("N", m, n, alpha, a, lda, x, 1, beta, y, 1, 0, False, 0)
+                w1 = oracle.exgemv("N", m, n, alpha, a, lda, x, 1, beta, y, 1, 0, False, 1)
+                da, dx = torch.from_numpy(a).cuda(), torch.from_numpy(x).cuda()
+                for fpe, ee in VARIANTS:
+                    for rm, want in ((0, w0), (1, w1)):
+                        dy = torch.from_numpy(y).cuda()
+                        xb.exgemv("N", m, n, alpha, da, lda, 0, dx, 1, 0, beta, dy, 1, 0, fpe, ee, round_mode=rm, handle=gpu)
+                        got = dy.cpu().numpy()
+                        assert (got.view(np.uint64) == want.view(np.uint64)).all(), (m, n, kind, alpha, beta, fpe, ee, rm)
+                # host pointers (what the reference's exgemv takes)
+                hy = y.copy()
+                xb.exgemv("N", m, n, alpha, a, lda, 0, x, 1, 0, beta, hy, 1, 0, 4, False, handle=gpu)
+                assert (hy.view(np.uint64) == w0.view(np.uint64)).all()
+    assert gpu.last_status() == 0
+
+
+@pytest.mark.gpu
+def test_exgemv_offsets_strides_and_splits(gpu, oracle):
+    import torch
+    import exblas_b200 as xb
+    m, n, lda = 300, 777, 320
+    a, x, y = make(m, n, lda, "loguniform", seed=11)
+    offa, offx, offy, incx, incy = 5, 3, 2, 2, 3
+    abuf = np.concatenate([np.full(offa, 9.0), a])
+    xbuf = np.full(offx + (n - 1) * incx + 1, 7.0)
+    xbuf[offx::incx][:n] = x
+    ybuf = np.full(offy + (m - 1) * incy + 1, 5.0)
+    ybuf[offy::incy][:m] = y
+    want = oracle.exgemv("N", m, n, 1.0, a, lda, x, 1, 1.0, y, 1, 0, False, 0)
+    try:
+        for parts in (0, 1, 2, 7, 13):
+            gpu.set_option("gemv_parts", parts)
+            for fpe, ee in [(0, False), (3, False), (8, True)]:
+                dy = torch.from_numpy(ybuf.copy()).cuda()
+                xb.exgemv("N", m, n, 1.0, torch.from_numpy(abuf).cuda(), lda, offa, torch.from_numpy(xbuf).cuda(), incx, offx,
+                          1.0, dy, incy, offy, fpe, ee, handle=gpu)
+                out = dy.cpu().numpy()
+                assert (out[offy::incy][:m].view(np.uint64) == want.view(np.uint64)).all(), (parts, fpe, ee)
+                mask = np.ones(out.size, dtype=bool)
+                mask[offy::incy] = False
+                assert (out[mask] == 5.0).all()                      # nothing else touched
+    finally:
+        gpu.set_option("gemv_parts", 0)
+
+
+@pytest.mark.gpu
+def test_exgemv_large_rows_match_exdot(gpu):
+    """size-independent property at a BASELINE-like shape: every row of exgemv equals exdot of that row"""
+    import torch
+    import exblas_b200 as xb
+    m, n = 4096, 8192
+    A = cm.init_fpuniform(m * n, 664, 332, seed=3, neg_ratio=2, device="cuda")      # column-major m x n
+    x = cm.init_fpuniform(n, 100, 50, seed=4, neg_ratio=2, device="cuda")
+    y = torch.zeros(m, dtype=torch.float64, device="cuda")
+    xb.exgemv("N", m, n, 1.0, A, m, 0, x, 1, 0, 0.0, y, 1, 0, 8, True, handle=gpu)
+    rows = [0, 1, 511, 512, 2047, 4095]
+    Am = A.view(n, m)
+    for r in rows:
+        row = Am[:, r].contiguous()
+        gpu.exdot_async(n, row, 1, 0, x, 1, 0, 3, False, 0)
+        v, _, st = gpu.fetch()
+        assert v == float(y[r]) and st == 0, r
+    # naive closed form: every entry 1.1 * 1.1 summed n times
+    A.fill_(1.1)
+    x.fill_(1.1)
+    xb.exgemv("N", m, n, 1.0, A, m, 0, x, 1, 0, 0.0, y, 1, 0, 4, False, round_mode=xb.ROUND_EXACT, handle=gpu)
+    want = float(Fraction(1.1) * Fraction(1.1) * n)
+    assert bool((y == want).all())
