@@ -4,7 +4,7 @@
            early_exit=False) -> 0,  y overwritten with alpha*A*x + beta*y, every element the rounded
                                     exact value
 
-transa == 'N' is implemented (BASELINE config 5).  a, x, y: numpy float64 arrays (host, y is
+transa == 'N' is the tuned case (BASELINE config 5); 'T' is correct but not yet tuned.  a, x, y: numpy float64 arrays (host, y is
 updated in place) or torch CUDA float64 tensors (device pointers, asynchronous on the handle's
 stream; the wrapper synchronises before returning, like the reference).
 """
@@ -28,9 +28,11 @@ def exgemv(transa, m, n, alpha, a, lda, offseta, x, incx, offsetx, beta, y, incy
         raise ValueError("invalid m / n / lda / inc / offset")
     if m and n and offseta + lda * (n - 1) + m > sa:
         raise ValueError("a is too small for m, n, lda, offseta")
-    if n and offsetx + (n - 1) * incx >= sx:
+    tr = transa in (b"T", b"t")
+    nin, nout = (m, n) if tr else (n, m)
+    if nin and offsetx + (nin - 1) * incx >= sx:
         raise ValueError("x is too small")
-    if m and offsety + (m - 1) * incy >= sy:
+    if nout and offsety + (nout - 1) * incy >= sy:
         raise ValueError("y is too small")
     check(h.lib.exblas_b200_exgemv(h._h, transa, m, n, float(alpha), aa, lda, offseta, ax, incx, offsetx, float(beta),
                                    ay, incy, offsety, fpe, int(early_exit), round_mode), h._h)

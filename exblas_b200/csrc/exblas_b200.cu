@@ -362,7 +362,7 @@ int choose_gemv_parts(int64_t row_blocks, int64_t n, int num_sms) {
     return best;
 }
 
-int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, const double* a, int64_t lda,
+int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, const double* a, int64_t rs, int64_t cs,
                 const double* x, int64_t incx, double beta, double* y, int64_t incy, int f, bool ee, int round_mode) {
     int T = (int)h->opt_block_threads;
     if (m < T) T = (int)((m + 31) / 32 * 32);
@@ -388,7 +388,8 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     p.y = y;
     p.m = m;
     p.n = n;
-    p.lda = lda;
+    p.rs = rs;
+    p.cs = cs;
     p.incx = incx;
     p.incy = incy;
     p.alpha = alpha;
@@ -580,8 +581,9 @@ int exblas_b200_exgemv(exblas_b200_handle_t h, char trans, int64_t m, int64_t n,
                        int64_t lda, int64_t offseta, const double* x, int64_t incx, int64_t offsetx, double beta,
                        double* y, int64_t incy, int64_t offsety, int fpe, int early_exit, int round_mode) {
     if (!h) return EXBLAS_B200_EINVAL;
-    if (trans != 'N' && trans != 'n') {
-        h->err = "exgemv: only the non-transpose case ('N') is implemented";
+    const bool tr = (trans == 'T' || trans == 't');
+    if (!tr && trans != 'N' && trans != 'n') {
+        h->err = "exgemv: transa must be 'N' or 'T'";
         return EXBLAS_B200_EINVAL;
     }
     if (m < 0 || n < 0 || lda < (m > 1 ? m : 1) || incx < 1 || incy < 1 || fpe < 0 || offseta < 0 || offsetx < 0 ||
@@ -589,7 +591,9 @@ int exblas_b200_exgemv(exblas_b200_handle_t h, char trans, int64_t m, int64_t n,
         h->err = "exgemv: invalid argument";
         return EXBLAS_B200_EINVAL;
     }
-    if (m == 0) return EXBLAS_B200_OK;
+    const int64_t mo = tr ? n : m, ni = tr ? m : n;          // outputs, summands per output
+    const int64_t rs = tr ? lda : 1, cs = tr ? 1 : lda;
+    if (mo == 0) return EXBLAS_B200_OK;
     CK(cudaSetDevice(h->device));
     // fpe: 0 superaccumulators only; 1 is the reference's plain (non-reproducible) DGEMV comparator
     // (ExGEMV.cpp:92-94) -- here it also runs the exact superaccumulator kernel; early exit buckets 4/6/8.
@@ -598,16 +602,16 @@ int exblas_b200_exgemv(exblas_b200_handle_t h, char trans, int64_t m, int64_t n,
     const double* pa = a ? a + offseta : a;
     const double* px = x ? x + offsetx : x;
     double* py = y + offsety;
-    const bool dev = is_device_pointer(py) && (n == 0 || (is_device_pointer(pa) && is_device_pointer(px)));
+    const bool dev = is_device_pointer(py) && (ni == 0 || m == 0 || n == 0 || (is_device_pointer(pa) && is_device_pointer(px)));
     int rc;
     if (dev) {
-        rc = gemv_device(h, m, n, alpha, pa, lda, px, incx, beta, py, incy, f, ee, round_mode);
+        rc = gemv_device(h, mo, ni, alpha, pa, rs, cs, px, incx, beta, py, incy, f, ee, round_mode);
         if (rc) return rc;
     } else {
         // host operands (what the reference's exgemv takes, ExGEMV.cpp:109-234): stage on the device
         double *da = nullptr, *dx = nullptr, *dy = nullptr;
-        const size_t na = n > 0 ? (size_t)lda * (n - 1) + m : 0, nx = n > 0 ? (size_t)(n - 1) * incx + 1 : 0,
-                     ny = (size_t)(m - 1) * incy + 1;
+        const size_t na = (n > 0 && m > 0) ? (size_t)lda * (n - 1) + m : 0, nx = ni > 0 ? (size_t)(ni - 1) * incx + 1 : 0,
+                     ny = (size_t)(mo - 1) * incy + 1;
         rc = [&]() -> int {
             if (na) CK(cudaMalloc(&da, na * sizeof(double)));
             if (nx) CK(cudaMalloc(&dx, nx * sizeof(double)));
@@ -615,7 +619,7 @@ int exblas_b200_exgemv(exblas_b200_handle_t h, char trans, int64_t m, int64_t n,
             if (na) CK(cudaMemcpyAsync(da, pa, na * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             if (nx) CK(cudaMemcpyAsync(dx, px, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(dy, py, ny * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            int r2 = gemv_device(h, m, n, alpha, da, lda, dx, incx, beta, dy, incy, f, ee, round_mode);
+            int r2 = gemv_device(h, mo, ni, alpha, da, rs, cs, dx, incx, beta, dy, incy, f, ee, round_mode);
             if (r2) return r2;
             CK(cudaMemcpyAsync(py, dy, ny * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));

@@ -1,4 +1,6 @@
-// gemv_kernel.cuh -- ExGEMV 'N' (y := alpha*A*x + beta*y, column-major A) for sm_100a.
+// gemv_kernel.cuh -- ExGEMV (y := alpha*op(A)*x + beta*y, column-major A) for sm_100a.
+// 'N' is the tuned case (coalesced); 'T' runs the same kernel with the strides swapped (correct,
+// uncoalesced: SURVEY section 8f rank 3 leaves its fast path for later).
 //
 // SURVEY.md section 8f rank 1 / BASELINE config 5.  Replaces the reference's OpenCL kernels
 //   gemv / gemv_reduce   src/gpu/blas/blas2/ExGEMV.FPE.cl:199-379, 561-580, ExGEMV.FPE.EX.{4,6,8}.cl,
@@ -24,10 +26,10 @@
 namespace exb {
 
 struct GemvParams {
-    const double* a;        // already offset by offseta; element (i, j) at a[i + lda * j]
+    const double* a;        // already offset by offseta; output r, summand c reads a[r * rs + c * cs]
     const double* x;        // already offset by offsetx
     double* y;              // already offset by offsety
-    long long m, n, lda, incx, incy;
+    long long m, n, rs, cs, incx, incy;   // m outputs, n summands each ('N': rs = 1, cs = lda; 'T': rs = lda, cs = 1)
     double alpha, beta;
     long long cols_per_part;      // multiple of 4
     int parts;
@@ -72,15 +74,15 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
     const long long ngroups = ncols / 4;                     // full groups of 4 columns
     const bool unit_alpha = prm.alpha == 1.0;
     constexpr int kDepPerGroup = 4 * 2 * 2;                  // 4 columns, <= 2 products each when alpha != 1, 2 parts
-    const double* pa = prm.a + row + prm.lda * c0;
+    const double* pa = prm.a + row * prm.rs + prm.cs * c0;
     const double* px = prm.x + prm.incx * c0;
-    const long long astep = 4 * prm.lda, xstep = 4 * prm.incx;
+    const long long astep = 4 * prm.cs, xstep = 4 * prm.incx;
 
     double va[U][4], vx[U][4];
     auto load_group = [&](int u, const double* qa, const double* qx) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            va[u][k] = ldg64(qa + k * prm.lda);
+            va[u][k] = ldg64(qa + k * prm.cs);
             vx[u][k] = __ldg(qx + k * prm.incx);             // same address in every lane: one L1 broadcast
         }
     };
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
     }
     // leftover columns (< 4)
     for (long long c = c0 + ngroups * 4; c < c1; ++c) {
-        const double av = prm.a[row + prm.lda * c], xv = prm.x[prm.incx * c];
+        const double av = prm.a[row * prm.rs + prm.cs * c], xv = prm.x[prm.incx * c];
         double xa[4] = {av, 0.0, 0.0, 0.0};
         const double xb[4] = {xv, 0.0, 0.0, 0.0};
         if (unit_alpha) {
