@@ -28,8 +28,13 @@ def build(force: bool = False) -> None:
     if force or not os.path.exists(ORACLE_SO) or \
             os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "exblas_oracle.c")):
         subprocess.check_call(["make", "-s", "-C", HERE, os.path.join(HERE, "liboracle.so")])
-    if os.path.isdir("/root/reference/src/cpu/blas/blas1") and (force or not os.path.exists(REF_SO)):
-        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+    if os.path.isdir("/root/reference/src/cpu/blas/blas1"):
+        if force or not os.path.exists(REF_SO):
+            subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        # the reference's own GPU test mains, linked against the product library (needs it built first)
+        prod = os.path.join(HERE, "..", "exblas_b200", "libexblas_b200.so")
+        if os.path.exists(prod) and (force or not os.path.exists(os.path.join(HERE, "_ref", "test.exsum.gpu"))):
+            subprocess.check_call(["make", "-s", "-C", HERE, "ref_tests"])
 
 
 def _as_f64(a) -> np.ndarray:
