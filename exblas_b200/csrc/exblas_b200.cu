@@ -317,30 +317,34 @@ int fetch_result(exblas_b200_handle_t h, double* result, int64_t* limbs, uint32_
 
 typedef void (*gemv_fn)(const GemvParams);
 
-constexpr int gemv_groups_in_flight(int f) { return f <= 4 ? 4 : 2; }
+// ExGEMV CTAs are 384 threads (one row each): the kernel needs ~150 registers per thread (pointers,
+// a deep window of 8-byte loads, the expansion), which a 512-thread CTA cannot have without spills.
+constexpr int kGemvT = 384;
+constexpr int gemv_groups_in_flight(int f) { return f <= 4 ? 4 : 3; }
 
-template <int F, bool EE>
+template <int F, bool EE, bool A1>
 gemv_fn gemv_ptr() {
-    return exgemv_n_kernel<F, EE, gemv_groups_in_flight(F), kMaxT>;
+    return exgemv_n_kernel<F, EE, A1, gemv_groups_in_flight(F), kGemvT>;
 }
 
+template <bool A1>
 gemv_fn select_gemv(int f, bool ee) {
     if (ee) {
         switch (f) {
-            case 4: return gemv_ptr<4, true>();
-            case 6: return gemv_ptr<6, true>();
-            default: return gemv_ptr<8, true>();
+            case 4: return gemv_ptr<4, true, A1>();
+            case 6: return gemv_ptr<6, true, A1>();
+            default: return gemv_ptr<8, true, A1>();
         }
     }
     switch (f) {
-        case 0: return gemv_ptr<0, false>();
-        case 2: return gemv_ptr<2, false>();
-        case 3: return gemv_ptr<3, false>();
-        case 4: return gemv_ptr<4, false>();
-        case 5: return gemv_ptr<5, false>();
-        case 6: return gemv_ptr<6, false>();
-        case 7: return gemv_ptr<7, false>();
-        default: return gemv_ptr<8, false>();
+        case 0: return gemv_ptr<0, false, A1>();
+        case 2: return gemv_ptr<2, false, A1>();
+        case 3: return gemv_ptr<3, false, A1>();
+        case 4: return gemv_ptr<4, false, A1>();
+        case 5: return gemv_ptr<5, false, A1>();
+        case 6: return gemv_ptr<6, false, A1>();
+        case 7: return gemv_ptr<7, false, A1>();
+        default: return gemv_ptr<8, false, A1>();
     }
 }
 
@@ -364,7 +368,7 @@ int choose_gemv_parts(int64_t row_blocks, int64_t n, int num_sms) {
 
 int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, const double* a, int64_t rs, int64_t cs,
                 const double* x, int64_t incx, double beta, double* y, int64_t incy, int f, bool ee, int round_mode) {
-    int T = (int)h->opt_block_threads;
+    int T = kGemvT;
     if (m < T) T = (int)((m + 31) / 32 * 32);
     if (T < 32) T = 32;
     const int64_t row_blocks = (m + T - 1) / T;
@@ -401,7 +405,8 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     p.ws = h->d_ws;
     p.round_mode = round_mode;
     p.adaptive = h->opt_adaptive ? 1 : 0;
-    gemv_fn fn = select_gemv(f, ee);
+    p.x_vec_ok = (incx == 1 && ((uintptr_t)x % 32) == 0) ? 1 : 0;       // part starts are multiples of 4 columns
+    gemv_fn fn = alpha == 1.0 ? select_gemv<true>(f, ee) : select_gemv<false>(f, ee);
     const size_t smem = (size_t)T * kLimbs * sizeof(long long);
     CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {(void*)&p};
@@ -759,6 +764,12 @@ exblas_b200_handle_t default_handle() {
     });
     return h;
 }
+// The reference's examples call exsum() from several pthreads (RNGExample.cpp:549-556, with
+// parallel = false); the default handle shares one workspace, so the wrappers serialise on it.
+std::mutex& default_mutex() {
+    static std::mutex m;
+    return m;
+}
 int default_round_mode() {
     const char* e = getenv("EXBLAS_B200_ROUND");
     return (e && (!strcmp(e, "exact") || !strcmp(e, "1"))) ? EXBLAS_B200_ROUND_EXACT : EXBLAS_B200_ROUND_REFERENCE;
@@ -772,6 +783,7 @@ double exsum(const int Ng, double* ag, const int inca, const int offset, const i
         exit(1);
     }
     exblas_b200_handle_t h = default_handle();
+    std::lock_guard<std::mutex> lock(default_mutex());
     double r = 0.0;
     int rc = exblas_b200_exsum(h, ag, Ng < 0 ? 0 : Ng, inca, offset, fpe, early_exit ? 1 : 0, default_round_mode(), &r);
     if (rc != EXBLAS_B200_OK) {
@@ -789,6 +801,7 @@ double exdot(const int Ng, double* ag, const int inca, const int offseta, double
         exit(1);
     }
     exblas_b200_handle_t h = default_handle();
+    std::lock_guard<std::mutex> lock(default_mutex());
     double r = 0.0;
     int rc = exblas_b200_exdot(h, ag, inca, offseta, bg, incb, offsetb, Ng, fpe, early_exit ? 1 : 0,
                                default_round_mode(), &r);
@@ -803,6 +816,7 @@ int exgemv(const char transa, const int m, const int n, const double alpha, doub
            double* x, const int incx, const int offsetx, const double beta, double* y, const int incy, const int offsety,
            const int fpe, const bool early_exit) {
     exblas_b200_handle_t h = default_handle();
+    std::lock_guard<std::mutex> lock(default_mutex());
     int rc = exblas_b200_exgemv(h, transa, m, n, alpha, a, lda, offseta, x, incx, offsetx, beta, y, incy, offsety, fpe,
                                 early_exit ? 1 : 0, default_round_mode());
     if (rc == EXBLAS_B200_OK) rc = exblas_b200_sync(h);

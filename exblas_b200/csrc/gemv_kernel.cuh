@@ -38,7 +38,14 @@ struct GemvParams {
     Workspace* ws;
     int round_mode;
     int adaptive;
+    int x_vec_ok;           // x contiguous and 32-byte aligned at every part start
 };
+
+EXB_D Vec4 ldg256_cached(const double* p) {     // through L1: x is re-read by every warp of the CTA
+    Vec4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
 
 EXB_D double ldg64(const double* p) {
     double r;
@@ -46,7 +53,7 @@ EXB_D double ldg64(const double* p) {
     return r;
 }
 
-template <int F, bool EE, int U, int MAXT>
+template <int F, bool EE, bool ALPHA1, int U, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm) {
     extern __shared__ long long smem[];
     const unsigned T = blockDim.x;
@@ -72,60 +79,83 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
     if (c1 > prm.n) c1 = prm.n;
     const long long ncols = c1 > c0 ? c1 - c0 : 0;
     const long long ngroups = ncols / 4;                     // full groups of 4 columns
-    const bool unit_alpha = prm.alpha == 1.0;
+    constexpr bool unit_alpha = ALPHA1;                      // alpha == 1 (the only case the reference tests) is its own instantiation
     constexpr int kDepPerGroup = 4 * 2 * 2;                  // 4 columns, <= 2 products each when alpha != 1, 2 parts
     const double* pa = prm.a + row * prm.rs + prm.cs * c0;
     const double* px = prm.x + prm.incx * c0;
     const long long astep = 4 * prm.cs, xstep = 4 * prm.incx;
 
-    double va[U][4], vx[U][4];
-    auto load_group = [&](int u, const double* qa, const double* qx) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            va[u][k] = ldg64(qa + k * prm.cs);
-            vx[u][k] = __ldg(qx + k * prm.incx);             // same address in every lane: one L1 broadcast
+    // Rolling window of U column groups (4 columns each) of A per thread, refilled right after use.
+    // All addressing is by running pointers (no 64-bit multiplies in the loop).  x[k..k+3] is one
+    // 256-bit broadcast load when x is contiguous and 32-byte aligned (every lane reads the same
+    // address: one L1 wavefront), else four scalar broadcast loads.
+    double va[U][4];
+    Vec4 vx[U];
+    const long long cs = prm.cs, incx = prm.incx;
+    const bool xvec = prm.x_vec_ok != 0;
+    const double* qa = pa;                                   // next group of A to load
+    const double* qx = px;                                   // next group of x to load
+    auto load_group = [&](int u) {
+        va[u][0] = ldg64(qa);
+        va[u][1] = ldg64(qa + cs);
+        va[u][2] = ldg64(qa + 2 * cs);
+        va[u][3] = ldg64(qa + 3 * cs);
+        if (xvec) {
+            vx[u] = ldg256_cached(qx);
+        } else {
+            vx[u].x = __ldg(qx);
+            vx[u].y = __ldg(qx + incx);
+            vx[u].z = __ldg(qx + 2 * incx);
+            vx[u].w = __ldg(qx + 3 * incx);
         }
+        qa += astep;
+        qx += xstep;
     };
+    const long long rounds = ngroups / U;                    // full rounds of U groups
 #pragma unroll
     for (int u = 0; u < U; ++u)
-        if (u < ngroups) load_group(u, pa + u * astep, px + u * xstep);
+        if (rounds > 0) load_group(u);
 
     int since_norm = 0;
     int bypass = 0, backoff = kBypassTiles;
-    for (long long g = 0; g < ngroups; g += U) {
+    auto consume = [&](const double (&xa_in)[4], const Vec4& xv, bool direct, int& deposits) {
+        double xa[4] = {xa_in[0], xa_in[1], xa_in[2], xa_in[3]};
+        const double xb[4] = {xv.x, xv.y, xv.z, xv.w};
+        if constexpr (unit_alpha) {
+            if (direct) {
+                double none[1][expansions(0)];
+                mul_add4<0, false, true>(col, stride, none, status, xa, xb);
+            } else {
+                deposits += mul_add4<F, EE, true>(col, stride, a, status, xa, xb);
+            }
+        } else {
+            // alpha * a = p1 + e1 exactly; then p1 * x and e1 * x
+            double p1[4], e1[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                p1[k] = __dmul_rn(prm.alpha, xa[k]);
+                e1[k] = __fma_rn(prm.alpha, xa[k], -p1[k]);
+            }
+            if (direct) {
+                double none[1][expansions(0)];
+                mul_add4<0, false, true>(col, stride, none, status, p1, xb);
+                mul_add4<0, false, true>(col, stride, none, status, e1, xb);
+            } else {
+                deposits += mul_add4<F, EE, true>(col, stride, a, status, p1, xb);
+                deposits += mul_add4<F, EE, true>(col, stride, a, status, e1, xb);
+            }
+        }
+    };
+    for (long long r = 0; r < rounds; ++r) {
         const bool direct = (F == 0) || (prm.adaptive && bypass > 0);
+        const bool has_next = r + 1 < rounds;
         int deposits = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (g + u < ngroups) {
-                double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
-                double xb[4] = {vx[u][0], vx[u][1], vx[u][2], vx[u][3]};
-                if (g + u + U < ngroups) load_group(u, pa + (g + u + U) * astep, px + (g + u + U) * xstep);
-                if (unit_alpha) {
-                    if (direct) {
-                        double none[1][expansions(0)];
-                        mul_add4<0, false, true>(col, stride, none, status, xa, xb);
-                    } else {
-                        deposits += mul_add4<F, EE, true>(col, stride, a, status, xa, xb);
-                    }
-                } else {
-                    // alpha * a = p1 + e1 exactly; then p1 * x and e1 * x
-                    double p1[4], e1[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        p1[k] = __dmul_rn(prm.alpha, xa[k]);
-                        e1[k] = __fma_rn(prm.alpha, xa[k], -p1[k]);
-                    }
-                    if (direct) {
-                        double none[1][expansions(0)];
-                        mul_add4<0, false, true>(col, stride, none, status, p1, xb);
-                        mul_add4<0, false, true>(col, stride, none, status, e1, xb);
-                    } else {
-                        deposits += mul_add4<F, EE, true>(col, stride, a, status, p1, xb);
-                        deposits += mul_add4<F, EE, true>(col, stride, a, status, e1, xb);
-                    }
-                }
-            }
+            double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
+            const Vec4 xv = vx[u];
+            if (has_next) load_group(u);
+            consume(xa, xv, direct, deposits);
         }
         if (F > 0 && prm.adaptive) {
             if (bypass > 0) {
@@ -141,17 +171,28 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
             }
         }
         since_norm += U * kDepPerGroup;
-        if (since_norm > kMaxDepositsPerNormalize - U * kDepPerGroup - 2 * kM * (F + 2) - 32) {
+        if (since_norm > kMaxDepositsPerNormalize - U * kDepPerGroup - 2 * kM * (F + 2) - 64) {
             normalize_column(col, stride);
             since_norm = 0;
         }
     }
+    // groups left over after the full rounds (< U of them), then columns left over (< 4)
+    for (long long g = rounds * U; g < ngroups; ++g) {
+        const double* ra = pa + g * astep;
+        const double* rx = px + g * xstep;
+        double xa[4] = {ra[0], ra[cs], ra[2 * cs], ra[3 * cs]};
+        Vec4 xv;
+        xv.x = rx[0]; xv.y = rx[incx]; xv.z = rx[2 * incx]; xv.w = rx[3 * incx];
+        int deposits = 0;
+        consume(xa, xv, F == 0, deposits);
+    }
+    normalize_column(col, stride);
     // leftover columns (< 4)
     for (long long c = c0 + ngroups * 4; c < c1; ++c) {
         const double av = prm.a[row * prm.rs + prm.cs * c], xv = prm.x[prm.incx * c];
         double xa[4] = {av, 0.0, 0.0, 0.0};
         const double xb[4] = {xv, 0.0, 0.0, 0.0};
-        if (unit_alpha) {
+        if constexpr (unit_alpha) {
             mul_add4<F, EE, false>(col, stride, a, status, xa, xb);
         } else {
             double p1[4] = {__dmul_rn(prm.alpha, av), 0.0, 0.0, 0.0};

@@ -78,3 +78,21 @@ def test_cancelling_dot_2p30_known_answer(gpu):
         gpu.exdot_async(N, a, 1, 0, b, 1, 0, fpe, ee, 1)
         v, l, st = gpu.fetch()
         assert v == 1.5 and st == 0, (fpe, ee)
+
+
+def test_naive_closed_form_2p32(gpu):
+    """BASELINE config 4's largest size: 2^32 doubles (32 GiB) -- 64-bit lengths end to end"""
+    import torch
+    n = 1 << 32
+    free, _ = torch.cuda.mem_get_info()
+    if free < (n * 8) + (2 << 30):
+        pytest.skip("not enough free device memory for a 32 GiB vector")
+    a = torch.full((n,), 1.1, dtype=torch.float64, device="cuda")
+    a[n - 1] = -3.25                                         # the very last element must be seen
+    exact = Fraction(1.1) * (n - 1) + Fraction(-3.25)
+    want = limbs_from_fraction(exact)
+    for fpe, ee in [(0, False), (3, False), (8, True)]:
+        v, l, st = _sum(gpu, a, fpe, ee, rm=1)
+        assert st == 0 and (l == want).all() and v == float(exact), (fpe, ee)
+    del a
+    torch.cuda.empty_cache()
