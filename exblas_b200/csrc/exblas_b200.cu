@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_set>
 
 #include "../../include/exblas_b200.h"
 #include "reduce_kernel.cuh"
@@ -109,11 +110,25 @@ struct exblas_b200_handle_s {
     void* comm = nullptr;
     int nranks = 1;
     int64_t launches = 0;
+    bool acc_pending = false;               // workspace accumulator holds an unfinished (chunked) reduction
     uint32_t last_status = 0;
     std::string err;
 };
 
 namespace {
+
+// cudaFuncSetAttribute is a slow driver call; do it once per kernel (per device) with the largest
+// shared-memory size this library ever asks for.
+cudaError_t allow_big_smem(const void* fn, int device) {
+    static std::mutex mu;
+    static std::unordered_set<uint64_t> done;
+    const uint64_t key = (uint64_t)(uintptr_t)fn * 131u + (uint64_t)device;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count(key)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * kLimbs * (int)sizeof(long long));
+    if (e == cudaSuccess) done.insert(key);
+    return e;
+}
 
 int fail_cuda(exblas_b200_handle_t h, cudaError_t e, const char* what) {
     if (h) h->err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -177,9 +192,17 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     p.round_mode = round_mode;
     p.keep = 0;
     p.adaptive = h->opt_adaptive ? 1 : 0;
+    p.fresh = h->acc_pending ? 0 : 1;
+    h->acc_pending = finalize ? false : true;      // an open (chunked) reduction leaves its partial sum in gacc
 
     int T = (int)h->opt_block_threads;
-    if (n <= (1 << 16)) T = 128;                       // latency regime: small CTAs, little smem to clear
+    int64_t max_blocks = h->opt_blocks > 0 ? h->opt_blocks : h->num_sms;
+    if (h->opt_blocks == 0) {
+        // latency regime: one CTA publishes straight from shared memory (no global merge round trip)
+        if (n <= (1 << 13)) { T = 128; max_blocks = 1; }
+        else if (n <= (1 << 15)) { max_blocks = 1; }
+        else if (n <= (1 << 18)) { T = 128; }          // small CTAs, little shared memory to clear
+    }
     const int U = vectors_in_flight(f, ee, dot);
     const int64_t tile = (int64_t)T * 4 * U;
 
@@ -197,7 +220,7 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
             if (p.ntiles == 0) p.head = 0;
         }
     }
-    int64_t blocks = h->opt_blocks > 0 ? h->opt_blocks : h->num_sms;
+    int64_t blocks = max_blocks;
     int64_t want;
     if (p.ntiles > 0) want = p.ntiles;
     else want = (n + T - 1) / T;
@@ -206,7 +229,7 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
 
     kernel_fn fn = dot ? select_kernel<true>(f, ee) : select_kernel<false>(f, ee);
     const size_t smem = (size_t)T * kLimbs * sizeof(long long);
-    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(allow_big_smem((const void*)fn, h->device));
     void* args[] = {(void*)&p};
     CK(cudaLaunchKernel((const void*)fn, dim3((unsigned)blocks), dim3((unsigned)T), args, smem, h->stream));
     h->launches += 1;
@@ -240,8 +263,24 @@ int ensure_stage(exblas_b200_handle_t h, int64_t elems, bool dot) {
 
 // Host inputs: chunked H2D copies on the copy stream, overlapped with the reduction of the previous
 // chunk; every chunk adds into the same device accumulator, the last launch publishes.
+int reduce_from_host_impl(exblas_b200_handle_t h, bool dot, int f, bool ee, const double* a, int64_t inca, const double* b,
+                          int64_t incb, int64_t n, int round_mode);
+
 int reduce_from_host(exblas_b200_handle_t h, bool dot, int f, bool ee, const double* a, int64_t inca, const double* b,
                      int64_t incb, int64_t n, int round_mode) {
+    int rc = reduce_from_host_impl(h, dot, f, ee, a, inca, b, incb, n, round_mode);
+    if (rc != EXBLAS_B200_OK && h->acc_pending) {
+        // a failed chunked reduction must not leave its partial sum behind
+        cudaStreamSynchronize(h->stream);
+        cudaMemset(h->d_ws, 0, sizeof(Workspace));
+        cudaGetLastError();
+        h->acc_pending = false;
+    }
+    return rc;
+}
+
+int reduce_from_host_impl(exblas_b200_handle_t h, bool dot, int f, bool ee, const double* a, int64_t inca, const double* b,
+                          int64_t incb, int64_t n, int round_mode) {
     int64_t chunk = h->opt_host_chunk;
     if (chunk > n) chunk = n;
     const int64_t max_inc = dot ? (inca > incb ? inca : incb) : inca;
@@ -408,7 +447,7 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     p.x_vec_ok = (incx == 1 && ((uintptr_t)x % 32) == 0) ? 1 : 0;       // part starts are multiples of 4 columns
     gemv_fn fn = alpha == 1.0 ? select_gemv<true>(f, ee) : select_gemv<false>(f, ee);
     const size_t smem = (size_t)T * kLimbs * sizeof(long long);
-    CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(allow_big_smem((const void*)fn, h->device));
     void* args[] = {(void*)&p};
     CK(cudaLaunchKernel((const void*)fn, dim3((unsigned)row_blocks, (unsigned)parts), dim3((unsigned)T), args, smem,
                         h->stream));

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
         }
         since_norm += U * kDepPerGroup;
         if (since_norm > kMaxDepositsPerNormalize - U * kDepPerGroup - 2 * kM * (F + 2) - 64) {
-            normalize_column(col, stride);
+            bound_column(col, stride);
             since_norm = 0;
         }
     }
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
         int deposits = 0;
         consume(xa, xv, F == 0, deposits);
     }
-    normalize_column(col, stride);
+    bound_column(col, stride);
     // leftover columns (< 4)
     for (long long c = c0 + ngroups * 4; c < c1; ++c) {
         const double av = prm.a[row * prm.rs + prm.cs * c], xv = prm.x[prm.incx * c];
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
 #pragma unroll
             for (int m = 0; m < kM; ++m) deposit(col, stride, a[i][m], status);
     }
-    normalize_column(col, stride);
+    bound_column(col, stride);
     if (status && valid) atomicOr(&prm.ws->status, status);
     if (valid) prm.row_status[(long long)blockIdx.y * prm.m + row_raw] = status;
     // this thread's limbs -> scratch[part][limb][row]

@@ -57,6 +57,7 @@ struct ReduceParams {
     int round_mode;                      // 0 reference Round(), 1 exact RN-even
     int keep;                            // 1: do not reset the accumulator after publishing
     int adaptive;                        // 1: bypass the expansion while it thrashes (performance only)
+    int fresh;                           // 1: the workspace accumulator is known to be zero (no pending chunks)
 };
 
 EXB_D Vec4 ldg256(const double* p) {
@@ -236,6 +237,25 @@ EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][exp
     return cnt;
 }
 
+// Carry-normalise a 39-limb array that lives in shared memory: pull it into registers first so the
+// carry chain runs at ALU latency instead of shared-memory round trips.
+EXB_D bool normalize_shared(long long* limbs) {
+    long long r[kLimbs];
+#pragma unroll
+    for (int j = 0; j < kLimbs; ++j) r[j] = limbs[j];
+    long long carry = 0;
+#pragma unroll
+    for (int j = 0; j < kLimbs - 1; ++j) {
+        const long long v = r[j] + carry;
+        carry = v >> kDigits;
+        r[j] = v & kLimbMask;
+    }
+    r[kLimbs - 1] += carry;
+#pragma unroll
+    for (int j = 0; j < kLimbs; ++j) limbs[j] = r[j];
+    return r[kLimbs - 1] < 0;
+}
+
 // Sum one limb row over all T columns; result valid in lane 0.
 EXB_D long long row_sum(unsigned row_addr, unsigned T, unsigned lane) {
     long long s = 0;
@@ -262,6 +282,11 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
     const unsigned col = smem_base + 8u * tid;
     __shared__ long long block_limbs[kLimbs];
     __shared__ unsigned is_last;
+    __shared__ unsigned block_status;
+    // Latency regime: a single CTA reducing into an empty workspace publishes straight from shared
+    // memory -- no global atomics, fence or ticket.
+    const bool solo = (gridDim.x == 1) && prm.fresh && prm.finalize;
+    if (tid == 0) block_status = 0;
 
     for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
     // columns are thread-private: no barrier needed before use
@@ -354,11 +379,11 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
             }
             since_norm += kDepPerTile;
             if (since_norm > kMaxDepositsPerNormalize - kDepPerTile - 2 * kM * (F + 2)) {
-                normalize_column(col, stride);
+                bound_column(col, stride);
                 since_norm = 0;
             }
         }
-        normalize_column(col, stride);
+        bound_column(col, stride);
     }
 
     // ---------------- scalar part: alignment head, tail, or the whole strided vector ----------
@@ -380,7 +405,7 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
             }
             since_norm += kDepPerElem;
             if (since_norm > kMaxDepositsPerNormalize - kDepPerElem - 2 * kM * (F + 2)) {
-                normalize_column(col, stride);
+                bound_column(col, stride);
                 since_norm = 0;
             }
         }
@@ -391,42 +416,51 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
 #pragma unroll
             for (int m = 0; m < kM; ++m) deposit(col, stride, a[i][m], status);
     }
-    normalize_column(col, stride);
-    if (status) atomicOr(&prm.ws->status, status);
-    __syncthreads();
+    bound_column(col, stride);
+    __syncthreads();                                       // block_status initialised; all columns final
+    if (status) {
+        if (solo) atomicOr(&block_status, status);
+        else atomicOr(&prm.ws->status, status);
+    }
 
     // ---------------- block merge: 39 row sums -> normalise -> global accumulator --------------
     {
         const unsigned warp = tid >> 5, ln = tid & 31u, nwarps = T >> 5;
         for (unsigned j = warp; j < (unsigned)kLimbs; j += nwarps) {
-            const long long s = row_sum(smem_base + j * stride, T, ln);   // |s| < T * 2^52 <= 2^62
+            const long long s = row_sum(smem_base + j * stride, T, ln);   // |s| < T * (2^52 + 2^11) < 2^62
             if (ln == 0) block_limbs[j] = s;
         }
         __syncthreads();
-        if (tid == 0) normalize(block_limbs);
-        __syncthreads();
-        for (unsigned j = tid; j < (unsigned)kLimbs; j += T) {
-            const long long v = block_limbs[j];
-            if (v != 0) atomicAdd(&prm.ws->gacc[j], (unsigned long long)v);
+        if (!solo) {
+            if (tid == 0) normalize_shared(block_limbs);
+            __syncthreads();
+            for (unsigned j = tid; j < (unsigned)kLimbs; j += T) {
+                const long long v = block_limbs[j];
+                if (v != 0) atomicAdd(&prm.ws->gacc[j], (unsigned long long)v);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned ticket = atomicAdd(&prm.ws->counter, 1u);
+                is_last = (ticket == gridDim.x - 1);
+            }
+            __syncthreads();
         }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned ticket = atomicAdd(&prm.ws->counter, 1u);
-            is_last = (ticket == gridDim.x - 1);
-        }
-        __syncthreads();
     }
 
     // ---------------- last CTA: normalise the global accumulator, publish ----------------------
-    if (is_last) {
-        __threadfence();
-        for (unsigned j = tid; j < (unsigned)kLimbs; j += T)
-            block_limbs[j] = (long long)atomicExch(&prm.ws->gacc[j], 0ull);
-        __syncthreads();
+    if (solo || is_last) {
+        if (!solo) {
+            __threadfence();
+            for (unsigned j = tid; j < (unsigned)kLimbs; j += T)
+                block_limbs[j] = (long long)atomicExch(&prm.ws->gacc[j], 0ull);
+            __syncthreads();
+        }
         if (tid == 0) {
-            unsigned st = prm.finalize && !prm.keep ? atomicExch(&prm.ws->status, 0u) : atomicOr(&prm.ws->status, 0u);
-            const bool neg = normalize(block_limbs);
+            unsigned st;
+            if (solo) st = block_status;
+            else st = prm.finalize && !prm.keep ? atomicExch(&prm.ws->status, 0u) : atomicOr(&prm.ws->status, 0u);
+            const bool neg = normalize_shared(block_limbs);
             if (prm.finalize) {
                 Result* out = prm.out;
                 for (int j = 0; j < kLimbs; ++j) out->limbs[j] = block_limbs[j];
@@ -439,11 +473,11 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
                 out->status = st;
                 for (int k = 0; k < kFlagSlots; ++k) out->flagcnt[k] = (st >> k) & 1u;
             }
-            prm.ws->counter = 0;
+            if (!solo) prm.ws->counter = 0;
         }
         __syncthreads();
         // leave the (normalised) partial sum in the workspace unless this call closes the reduction
-        if (!prm.finalize || prm.keep)
+        if (!solo && (!prm.finalize || prm.keep))
             for (unsigned j = tid; j < (unsigned)kLimbs; j += T) prm.ws->gacc[j] = (unsigned long long)block_limbs[j];
     }
 }

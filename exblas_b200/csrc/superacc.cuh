@@ -53,9 +53,10 @@ enum : unsigned {
     kStTooSmall = 16u,   // bits below 2^-1040 were truncated: result no longer exact
 };
 
-// Limb deposits between two normalisations of one accumulator column: each deposit adds a digit
-// of magnitude <= 2^52 to a limb that starts in [0, 2^52), so 2046 deposits keep |limb| < 2^63.
-constexpr int kMaxDepositsPerNormalize = 2046;
+// Limb deposits between two boundings of one accumulator column (bound_column): each deposit adds a
+// digit of magnitude <= 2^52 to a limb that starts below 2^52 + 2^11 in magnitude, so 2040 deposits
+// keep |limb| < 2^63.
+constexpr int kMaxDepositsPerNormalize = 2040;
 
 // ---------------------------------------------------------------------------------------------
 // host + device: normal form and the two finalisers
@@ -358,15 +359,19 @@ EXB_D void deposit4(unsigned col, unsigned stride, double x0, double x1, double 
     }
 }
 
-// Normalise a thread-private column in place (same normal form as normalize()).
-EXB_D void normalize_column(unsigned col, unsigned stride) {
+// Bound a thread-private column in place WITHOUT a carry chain: every limb keeps its low 52 bits
+// and receives the carry-save bits of the limb below (one step, no propagation).  The value is
+// unchanged and afterwards |limb| < 2^52 + 2^11, which is all the deposit budget (2046 more
+// digits) and the block merge (sum of <= 1024 columns) need.  Unlike a full normalisation the 39
+// steps are independent, so the shared-memory latency pipelines instead of adding up.
+EXB_D void bound_column(unsigned col, unsigned stride) {
     long long carry = 0;
     unsigned a = col;
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < kLimbs - 1; ++j, a += stride) {
-        const long long v = (long long)lds64(a) + carry;
+        const long long v = (long long)lds64(a);
+        sts64(a, (unsigned long long)((v & kLimbMask) + carry));
         carry = v >> kDigits;
-        sts64(a, (unsigned long long)(v & kLimbMask));
     }
     sts64(a, lds64(a) + (unsigned long long)carry);
 }
