@@ -6,7 +6,8 @@
     torchrun ... bench.py --gpus N ...          (N > 1: one rank per GPU)
 
 Workload (default = BASELINE.json configs[1]): ExSUM of 2^30 doubles (8 GiB), log-uniform
-1e-100..1e100 (init_fpuniform(n, 664, 332), random sign), FPE sizes 3, 4 and 8.  One STEP = one
+1e-100..1e100 (the reference's init_fpuniform(n, 664, 332), positive values; --dist
+loguniform_signed gives the same magnitudes with random signs), FPE sizes 3, 4 and 8.  One STEP = one
 reduction per FPE size over the same resident vector, i.e. 3 kernel launches and 3 x 8 GiB of
 algorithmic traffic.  `value` = algorithmic bytes / device time (CUDA events on the launching
 stream, inputs resident in HBM, 8 GiB >> 126 MB L2 so every pass streams from DRAM).
@@ -43,7 +44,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--op", default="exsum", choices=["exsum", "exdot"])
-    ap.add_argument("--dist", default="loguniform", choices=["loguniform", "naive", "illcond"])
+    ap.add_argument("--dist", default="loguniform", choices=["loguniform", "loguniform_signed", "naive", "illcond"])
     ap.add_argument("--log2n", type=int, default=30)
     ap.add_argument("--fpe", default="3,4,8")
     ap.add_argument("--early-exit", type=int, default=0)
@@ -57,13 +58,16 @@ def gen(dist, n_total, lo, hi, seed, device):
     from exblas_b200 import common as cm
     if dist == "naive":
         return cm.init_naive(n_total, lo=lo, hi=hi, device=device)
-    if dist == "loguniform":
+    if dist == "loguniform":            # the reference's generator: positive values (common.cpp:18-33, neg_ratio = 1)
+        return cm.init_fpuniform(n_total, 664, 332, seed=seed, neg_ratio=1, lo=lo, hi=hi, device=device)
+    if dist == "loguniform_signed":     # same magnitudes, random sign
         return cm.init_fpuniform(n_total, 664, 332, seed=seed, neg_ratio=2, lo=lo, hi=hi, device=device)
     return cm.init_ill_cond(n_total, 1e32, seed=seed, lo=lo, hi=hi, device=device)
 
 
 def workload_name(args, n):
-    d = {"loguniform": "log-uniform 1e-100..1e100 (init_fpuniform(n,664,332), random sign)",
+    d = {"loguniform": "log-uniform 1e-100..1e100 (the reference's init_fpuniform(n,664,332): positive values)",
+         "loguniform_signed": "log-uniform 1e-100..1e100 (init_fpuniform(n,664,332) magnitudes, random sign)",
          "naive": "all 1.1 (init_naive)", "illcond": "init_ill_cond(n, 1e32)"}[args.dist]
     return f"{args.op.upper()} n=2^{args.log2n} doubles per GPU, {d}, FPE sizes {args.fpe}" + \
         (" early-exit" if args.early_exit else "")

@@ -220,8 +220,8 @@ EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][exp
         }
     }
     if (F == 0) {
-        deposit4(col, stride, p[0], p[1], p[2], p[3], status);
-        deposit4(col, stride, e[0], e[1], e[2], e[3], status);     // zeros take the (cheap) slow path
+        deposit4<false>(col, stride, p[0], p[1], p[2], p[3], status);
+        deposit4<false>(col, stride, e[0], e[1], e[2], e[3], status);     // zeros take the (cheap) slow path
         return 0;
     }
     int cnt = 0;
@@ -330,19 +330,41 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
             // instruction cache): direct deposits, or the expansion walk.  Each vector slot is
             // refilled for the next tile right after it is consumed.
             if (direct) {
+                // ExSUM: one vote per tile on the signs of everything in the register window; an
+                // all-positive tile (the reference generator's data, norms, energies ...) takes the
+                // sign-free deposit, 7 integer instructions per element cheaper.
+                bool all_pos = false;
+#ifndef EXB_NO_POS
+                if (!DOT) {
+                    unsigned hs = 0u;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (DOT) {
-                        const double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
-                        const double y[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-                        double none[1][expansions(0)];
-                        mul_add4<0, false, true>(col, stride, none, status, x, y);
-                    } else {
-                        deposit4(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
+                    for (int u = 0; u < U; ++u)
+                        hs |= (unsigned)__double2hiint(va[u].x) | (unsigned)__double2hiint(va[u].y) |
+                              (unsigned)__double2hiint(va[u].z) | (unsigned)__double2hiint(va[u].w);
+                    all_pos = !__any_sync(0xffffffffu, (int)hs < 0);
+                }
+#endif
+                if (!DOT && all_pos) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        deposit4<true>(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
+                        if (has_next) va[u] = ldg256(pa + u * vstep);
                     }
-                    if (has_next) {
-                        va[u] = ldg256(pa + u * vstep);
-                        if (DOT) vb[u] = ldg256(pb + u * vstep);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (DOT) {
+                            const double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                            const double y[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+                            double none[1][expansions(0)];
+                            mul_add4<0, false, true>(col, stride, none, status, x, y);
+                        } else {
+                            deposit4<false>(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
+                        }
+                        if (has_next) {
+                            va[u] = ldg256(pa + u * vstep);
+                            if (DOT) vb[u] = ldg256(pb + u * vstep);
+                        }
                     }
                 }
             } else if (F > 0) {

@@ -301,6 +301,26 @@ EXB_D void deposit_fast(unsigned col, unsigned stride, unsigned lo, unsigned hi)
     sts64(a1, v1 + tm + ksel);
 }
 
+// Same for x > 0 only: no sign fix-ups at all (7 fewer integer instructions per element).  Used when
+// a whole warp's vector is positive, which is the reference generator's case (init_fpuniform,
+// common.cpp:18-33, draws positive values only) and that of norms, energies, histograms ...
+EXB_D void deposit_fast_pos(unsigned col, unsigned stride, unsigned lo, unsigned hi) {
+    const unsigned E = hi >> 20;                                   // sign bit is clear
+    const unsigned J1 = __umulhi(E + 17u, 82595525u);
+    const unsigned xhi = hi - J1 * (52u << 20) + (1040u << 20);
+    const double xs = __hiloint2double((int)xhi, (int)lo);
+    const double t = __dadd_rn(xs, 4503599627370496.0);
+    const double xr = __dsub_rn(t, 4503599627370496.0);
+    const double t2 = __dadd_rn(__dsub_rn(xs, xr), 1.5);
+    const unsigned long long d0 = (unsigned long long)__double_as_longlong(t2) - 0x3FF8000000000000ull;
+    const unsigned long long d1 = (unsigned long long)__double_as_longlong(t) - 0x4330000000000000ull;
+    const unsigned a1 = col + J1 * stride;
+    const unsigned a0 = (col - stride) + J1 * stride;
+    const unsigned long long v0 = lds64(a0), v1 = lds64(a1);
+    sts64(a0, v0 + d0);
+    sts64(a1, v1 + d1);
+}
+
 // distance of |x| above the lower edge of the fast range, as an unsigned 32-bit key on the high
 // word (so that one unsigned compare tests both edges, and a max over several keys tests them all)
 EXB_D unsigned range_key(unsigned hi) { return (hi & 0x7fffffffu) - (kEMin << 20); }
@@ -343,14 +363,23 @@ EXB_D void deposit(unsigned col, unsigned stride, double x, unsigned& status) {
 }
 
 // Four independent doubles; one range test for all of them (the common case is all-fast).
+// POS: the caller has established (warp vote over a whole tile) that no value is negative.
+template <bool POS>
 EXB_D void deposit4(unsigned col, unsigned stride, double x0, double x1, double x2, double x3, unsigned& status) {
     const unsigned h0 = (unsigned)__double2hiint(x0), h1 = (unsigned)__double2hiint(x1);
     const unsigned h2 = (unsigned)__double2hiint(x2), h3 = (unsigned)__double2hiint(x3);
     if (max(max(range_key(h0), range_key(h1)), max(range_key(h2), range_key(h3))) < kRangeSpan) {
-        deposit_fast(col, stride, (unsigned)__double2loint(x0), h0);
-        deposit_fast(col, stride, (unsigned)__double2loint(x1), h1);
-        deposit_fast(col, stride, (unsigned)__double2loint(x2), h2);
-        deposit_fast(col, stride, (unsigned)__double2loint(x3), h3);
+        if (POS) {
+            deposit_fast_pos(col, stride, (unsigned)__double2loint(x0), h0);
+            deposit_fast_pos(col, stride, (unsigned)__double2loint(x1), h1);
+            deposit_fast_pos(col, stride, (unsigned)__double2loint(x2), h2);
+            deposit_fast_pos(col, stride, (unsigned)__double2loint(x3), h3);
+        } else {
+            deposit_fast(col, stride, (unsigned)__double2loint(x0), h0);
+            deposit_fast(col, stride, (unsigned)__double2loint(x1), h1);
+            deposit_fast(col, stride, (unsigned)__double2loint(x2), h2);
+            deposit_fast(col, stride, (unsigned)__double2loint(x3), h3);
+        }
     } else {
         deposit(col, stride, x0, status);
         deposit(col, stride, x1, status);

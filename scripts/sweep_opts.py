@@ -11,6 +11,7 @@ h = xb.Handle(0)
 s = torch.cuda.Stream(); torch.cuda.set_stream(s); h.set_stream(s.cuda_stream)
 data = {"logu": cm.init_fpuniform(n, 664, 332, seed=1, neg_ratio=2, device=dev), "naive": cm.init_naive(n, device=dev)}
 data["ill"] = cm.init_ill_cond(n, 1e32, seed=1, device=dev)
+data["logupos"] = cm.init_fpuniform(n, 664, 332, seed=1, device=dev)
 b = cm.init_ill_cond(n, 1e32, seed=2, device=dev)
 torch.cuda.synchronize()
 def timeit(fn, reps=5):
@@ -20,9 +21,9 @@ def timeit(fn, reps=5):
     for _ in range(reps): fn()
     e1.record(s); e1.synchronize()
     return e0.elapsed_time(e1) / reps
-cfgs = [("exsum", "logu", 0, 0), ("exsum", "logu", 3, 0), ("exsum", "logu", 4, 0), ("exsum", "logu", 8, 0), ("exsum", "naive", 2, 0), ("exsum", "naive", 3, 0), ("exsum", "naive", 4, 0),
+cfgs = [("exsum", "logupos", 0, 0), ("exsum", "logupos", 3, 0), ("exsum", "logupos", 8, 0), ("exsum", "logu", 0, 0), ("exsum", "logu", 3, 0), ("exsum", "logu", 4, 0), ("exsum", "logu", 8, 0), ("exsum", "naive", 2, 0), ("exsum", "naive", 3, 0), ("exsum", "naive", 4, 0),
         ("exsum", "naive", 8, 0), ("exsum", "naive", 8, 1), ("exsum", "ill", 8, 1), ("exdot", "ill", 0, 0), ("exdot", "ill", 3, 0), ("exdot", "ill", 8, 0), ("exdot", "ill", 8, 1)]
-for pf in [1, 0]:
+for pf in [1]:
     h.set_option("adaptive", pf)
     row = []
     for op, kind, fpe, ee in cfgs:
