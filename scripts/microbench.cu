@@ -73,6 +73,15 @@ int main() {
         cudaEventElapsedTime(&ms, e0, e1);
         printf("{\"read_stream_GBs\": %.1f, \"threads\": %d, \"blocks\": %d}\n", 5.0 * (double)((size_t)1 << 33) / (ms * 1e-3) / 1e9, T, blocks);
     }
+    // 2b. the same stream sustained for ~0.5 s (power cap / clock effects), T = 512
+    {
+        int blocks = sms * 4;
+        cudaEventRecord(e0);
+        for (int r = 0; r < 400; ++r) read_kernel<<<blocks, 512>>>(d, nvec, d);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("{\"read_stream_sustained_GBs\": %.1f, \"seconds\": %.3f}\n", 400.0 * (double)((size_t)1 << 33) / (ms * 1e-3) / 1e9, ms * 1e-3);
+    }
     // 3. shared RMW
     cudaFuncSetAttribute(rmw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 39 * 8);
     rmw_kernel<<<sms, 512, 512 * 39 * 8>>>(100, lo); cudaDeviceSynchronize();
