@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
                 const int total = __reduce_add_sync(0xffffffffu, deposits);
                 if (total * 64 >= 32 * U * kDepPerGroup) {
                     bypass = backoff;
-                    backoff = min(backoff * 2, kBypassMax);
+                    backoff = min(backoff * 16, kBypassMax);   // a second thrashing probe in a row: stay away for long
                 } else {
                     backoff = kBypassTiles;
                 }
@@ -190,15 +190,13 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
     // leftover columns (< 4)
     for (long long c = c0 + ngroups * 4; c < c1; ++c) {
         const double av = prm.a[row * prm.rs + prm.cs * c], xv = prm.x[prm.incx * c];
-        double xa[4] = {av, 0.0, 0.0, 0.0};
-        const double xb[4] = {xv, 0.0, 0.0, 0.0};
         if constexpr (unit_alpha) {
-            mul_add4<F, EE, false>(col, stride, a, status, xa, xb);
+            mul_add1<F, EE>(col, stride, a, status, av, xv);
         } else {
-            double p1[4] = {__dmul_rn(prm.alpha, av), 0.0, 0.0, 0.0};
-            double e1[4] = {__fma_rn(prm.alpha, av, -p1[0]), 0.0, 0.0, 0.0};
-            mul_add4<F, EE, false>(col, stride, a, status, p1, xb);
-            mul_add4<F, EE, false>(col, stride, a, status, e1, xb);
+            const double p1 = __dmul_rn(prm.alpha, av);
+            const double e1 = __fma_rn(prm.alpha, av, -p1);
+            mul_add1<F, EE>(col, stride, a, status, p1, xv);
+            mul_add1<F, EE>(col, stride, a, status, e1, xv);
         }
     }
     if (F > 0) {

@@ -116,6 +116,19 @@ EXB_D void fpe_push4(double (&a)[F > 0 ? F : 1][expansions(F)], double (&x)[4], 
     }
 }
 
+// One summand through the levels [first, F) of expansion 0 (alignment heads, tails and strided
+// vectors; lanes are not converged there, so the early exit is per thread).
+template <int F, bool EE>
+EXB_D double fpe_push1(double (&a)[F > 0 ? F : 1][expansions(F)], double x, int first) {
+#pragma unroll
+    for (int i = 0; i < F; ++i) {
+        if (i < first) continue;
+        two_sum(a[i][0], x);
+        if (EE && i + 1 < F && !nonzero_bits(x)) break;
+    }
+    return x;
+}
+
 // Residuals that fell off the last level go to the superaccumulator column.  Returns how many.
 EXB_D int deposit_residuals(unsigned col, unsigned stride, const double (&x)[4], unsigned& status) {
     int cnt = 0;
@@ -235,6 +248,43 @@ EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][exp
           (unsigned)nonzero_bits(e[3]);
     if (any) cnt += deposit_residuals(col, stride, e, status);
     return cnt;
+}
+
+// Scalar versions for the non-vector part (one element per thread and iteration).
+template <int F, bool EE>
+EXB_D void add1(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][expansions(F)], unsigned& status, double x) {
+    if (F == 0) {
+        deposit(col, stride, x, status);
+        return;
+    }
+    const unsigned hi = (unsigned)__double2hiint(x);
+    if ((hi & 0x7fffffffu) >= (kELim << 20)) {                   // Inf / NaN / too large: keep out of the expansion
+        status |= deposit_slow(col, stride, (unsigned)__double2loint(x), hi);
+        return;
+    }
+    const double r = fpe_push1<F, EE>(a, x, 0);
+    if (nonzero_bits(r)) deposit(col, stride, r, status);
+}
+
+template <int F, bool EE>
+EXB_D void mul_add1(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][expansions(F)], unsigned& status, double x,
+                    double y) {
+    const double p = __dmul_rn(x, y);
+    const double e = __fma_rn(x, y, -p);
+    if ((((((unsigned)__double2hiint(p) & 0x7fffffffu) >> 20) - 88u)) >= (kELim - 88u)) {
+        status |= product_slow(col, stride, x, y, p, e);
+        return;
+    }
+    if (F == 0) {
+        deposit(col, stride, p, status);
+        deposit(col, stride, e, status);
+        return;
+    }
+    double r = fpe_push1<F, EE>(a, p, 0);
+    if (nonzero_bits(r)) deposit(col, stride, r, status);
+    constexpr int first = EE ? (F > 1 ? 1 : 0) : (F > 3 ? F - 3 : 0);
+    r = fpe_push1<F, EE>(a, e, first);
+    if (nonzero_bits(r)) deposit(col, stride, r, status);
 }
 
 // Carry-normalise a 39-limb array that lives in shared memory: pull it into registers first so the
@@ -393,7 +443,7 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
                     const int total = __reduce_add_sync(0xffffffffu, deposits);
                     if (total * 64 >= 32 * kDepPerTile) {
                         bypass = backoff;
-                        backoff = min(backoff * 2, kBypassMax);
+                        backoff = min(backoff * 16, kBypassMax);   // a second thrashing probe in a row: stay away for long
                     } else {
                         backoff = kBypassTiles;
                     }
@@ -416,15 +466,8 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
         int since_norm = 0;
         for (long long k = (long long)blockIdx.x * T + tid; k < nscalar; k += gthreads) {
             const long long idx = k < prm.head ? k : k + body;
-            double x[4] = {prm.a[idx * prm.inca], 0.0, 0.0, 0.0};
-            if (DOT) {
-                const double y[4] = {prm.b[idx * prm.incb], 0.0, 0.0, 0.0};
-                mul_add4<F, EE, false>(col, stride, a, status, x, y);
-            } else if (F == 0) {
-                deposit(col, stride, x[0], status);
-            } else {
-                add4<F, EE, false>(col, stride, a, status, x);
-            }
+            if (DOT) mul_add1<F, EE>(col, stride, a, status, prm.a[idx * prm.inca], prm.b[idx * prm.incb]);
+            else add1<F, EE>(col, stride, a, status, prm.a[idx * prm.inca]);
             since_norm += kDepPerElem;
             if (since_norm > kMaxDepositsPerNormalize - kDepPerElem - 2 * kM * (F + 2)) {
                 bound_column(col, stride);
