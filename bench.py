@@ -14,7 +14,8 @@ stream, inputs resident in HBM, 8 GiB >> 126 MB L2 so every pass streams from DR
 `e2e` = the same step through the synchronous C-ABI entry point with PINNED HOST buffers: H2D
 copies and the D2H read of the result are inside the timed region.
 N > 1: weak scaling -- every rank owns its own 2^30-element shard of an N * 2^30 vector, reduces
-it on its GPU and the ranks combine limbs exactly with a 44 x int64 NCCL all-reduce per reduction.
+it on its GPU and the ranks combine 44 x int64 (limbs + status counters) exactly: by default inside
+the closing kernel over NVLink peer memory (--collective fused), or with ncclAllReduce (--collective nccl).
 
 --impl reference times the reference's own CPU ExSUM (oracle/_ref, unmodified sources, OpenMP over
 all host cores; falls back to the oracle port if the prebuilt library is absent) on a bounded sample
@@ -48,6 +49,8 @@ def parse():
     ap.add_argument("--log2n", type=int, default=30)
     ap.add_argument("--fpe", default="3,4,8")
     ap.add_argument("--early-exit", type=int, default=0)
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: limb exchange inside the closing kernel over peer memory (fused) or ncclAllReduce")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the ExDOT (BASELINE config 3) side measurement")
@@ -247,6 +250,8 @@ def run_ours(args, fpes):
     if world > 1:
         red = xd.DistributedReducer(h)
         red.init_nccl()
+        if args.collective == "fused":
+            red.init_peer()
 
     a = gen(args.dist, n_total, rank * n, (rank + 1) * n, 1, dev)
     b = gen(args.dist, n_total, rank * n, (rank + 1) * n, 2, dev) if args.op == "exdot" else None
@@ -427,7 +432,8 @@ def run_ours(args, fpes):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, n), "elements_per_gpu": n, "launches_per_step": launches // args.steps,
                    "l2": "inputs (8 GiB per pass) are far larger than the 126 MB L2; no flush needed",
-                   "parallelism": f"shard{world}" if world > 1 else "single"},
+                   "parallelism": f"shard{world}" if world > 1 else "single",
+                   "collective": (args.collective if world > 1 else None)},
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "e2e": e2e,

@@ -46,6 +46,8 @@ SIGNATURES = {
     "exblas_b200_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "exblas_b200_comm_init": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p]),
     "exblas_b200_allreduce_async": (C.c_int, [_h, C.c_int]),
+    "exblas_b200_peer_export": (C.c_int, [_h, C.c_void_p]),
+    "exblas_b200_peer_attach": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p]),
     "exblas_b200_last_status": (C.c_int, [_h, C.POINTER(C.c_uint32)]),
     "exblas_b200_last_error": (C.c_char_p, [_h]),
     "exblas_b200_launch_count": (_i64, [_h]),

@@ -131,6 +131,17 @@ class Handle:
         check(self.lib.exblas_b200_comm_init(self._h, nranks, rank, buf), self._h)
         self.nranks = nranks
 
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self.lib.exblas_b200_peer_export(self._h, buf), self._h)
+        return buf.raw
+
+    def peer_attach(self, nranks: int, rank: int, handles) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == 64 * nranks
+        buf = C.create_string_buffer(blob, len(blob))
+        check(self.lib.exblas_b200_peer_attach(self._h, nranks, rank, buf), self._h)
+
     def allreduce_async(self, round_mode=ROUND_REFERENCE) -> None:
         check(self.lib.exblas_b200_allreduce_async(self._h, round_mode), self._h)
 

@@ -109,6 +109,12 @@ struct exblas_b200_handle_s {
     int64_t opt_gemv_parts = 0;
     void* comm = nullptr;
     int nranks = 1;
+    // fused peer-memory exchange (exblas_b200_peer_export / peer_attach)
+    Mailbox* d_mailbox = nullptr;           // this rank's mailbox (cudaMalloc: exportable through CUDA IPC)
+    Mailbox* peer_box[kMaxPeers] = {};      // every rank's mailbox mapped here (own entry = d_mailbox)
+    int peer_ranks = 0, peer_rank = 0;
+    unsigned long long epoch = 0;
+    int64_t opt_fused = 1;
     int64_t launches = 0;
     bool acc_pending = false;               // workspace accumulator holds an unfinished (chunked) reduction
     uint32_t last_status = 0;
@@ -193,6 +199,13 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     p.keep = 0;
     p.adaptive = h->opt_adaptive ? 1 : 0;
     p.fresh = h->acc_pending ? 0 : 1;
+    p.nranks = 0;
+    if (finalize && h->peer_ranks > 1 && h->opt_fused) {          // closing launch: exchange limbs inside the kernel
+        p.nranks = h->peer_ranks;
+        p.rank = h->peer_rank;
+        p.epoch = ++h->epoch;
+        for (int r = 0; r < h->peer_ranks; ++r) p.peers[r] = h->peer_box[r];
+    }
     h->acc_pending = finalize ? false : true;      // an open (chunked) reduction leaves its partial sum in gacc
 
     int T = (int)h->opt_block_threads;
@@ -418,7 +431,10 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     if (parts < 1) parts = 1;
     const size_t need = (size_t)parts * m * (kLimbs * sizeof(long long) + sizeof(unsigned));
     if (need > h->gemv_scratch_bytes) {
-        if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
+        for (int r = 0; r < h->peer_ranks; ++r)
+        if (h->peer_box[r] && h->peer_box[r] != h->d_mailbox) cudaIpcCloseMemHandle(h->peer_box[r]);
+    if (h->d_mailbox) cudaFree(h->d_mailbox);
+    if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
         h->d_gemv_scratch = nullptr;
         h->gemv_scratch_bytes = 0;
         CK(cudaMalloc(&h->d_gemv_scratch, need));
@@ -529,6 +545,9 @@ int exblas_b200_destroy(exblas_b200_handle_t h) {
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j)
             if (h->d_stage[i][j]) cudaFree(h->d_stage[i][j]);
+    for (int r = 0; r < h->peer_ranks; ++r)
+        if (h->peer_box[r] && h->peer_box[r] != h->d_mailbox) cudaIpcCloseMemHandle(h->peer_box[r]);
+    if (h->d_mailbox) cudaFree(h->d_mailbox);
     if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_res) cudaFree(h->d_res);
@@ -556,6 +575,8 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "blocks")) {
         if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;    // 2048 partials of < 2^52 fit a limb
         h->opt_blocks = value;
+    } else if (!strcmp(name, "fused_allreduce")) {
+        h->opt_fused = value != 0;
     } else if (!strcmp(name, "gemv_parts")) {
         if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;
         h->opt_gemv_parts = value;
@@ -750,9 +771,49 @@ int exblas_b200_comm_init(exblas_b200_handle_t h, int nranks, int rank, const vo
     return EXBLAS_B200_OK;
 }
 
+int exblas_b200_peer_export(exblas_b200_handle_t h, void* handle64) {
+    if (!h || !handle64) return EXBLAS_B200_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if (!h->d_mailbox) {
+        CK(cudaMalloc(&h->d_mailbox, sizeof(Mailbox)));
+        CK(cudaMemset(h->d_mailbox, 0, sizeof(Mailbox)));
+    }
+    cudaIpcMemHandle_t ipc;
+    CK(cudaIpcGetMemHandle(&ipc, h->d_mailbox));
+    static_assert(sizeof(ipc) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle64, &ipc, 64);
+    return EXBLAS_B200_OK;
+}
+
+int exblas_b200_peer_attach(exblas_b200_handle_t h, int nranks, int rank, const void* handles) {
+    if (!h || !handles || nranks < 1 || nranks > kMaxPeers || rank < 0 || rank >= nranks) return EXBLAS_B200_EINVAL;
+    if (!h->d_mailbox) {
+        h->err = "exblas_b200_peer_export must be called first";
+        return EXBLAS_B200_EINVAL;
+    }
+    CK(cudaSetDevice(h->device));
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            h->peer_box[r] = h->d_mailbox;
+            continue;
+        }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char*)handles + 64 * (size_t)r, 64);
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_box[r] = (Mailbox*)ptr;
+    }
+    h->peer_ranks = nranks;
+    h->peer_rank = rank;
+    h->epoch = 0;
+    return EXBLAS_B200_OK;
+}
+
 int exblas_b200_allreduce_async(exblas_b200_handle_t h, int round_mode) {
     if (!h) return EXBLAS_B200_EINVAL;
     CK(cudaSetDevice(h->device));
+    // with the fused exchange active the closing kernel has already merged and rounded
+    if (h->peer_ranks > 1 && h->opt_fused) return EXBLAS_B200_OK;
     if (h->nranks > 1) {
         if (!h->comm) {
             h->err = "exblas_b200_comm_init was not called";

@@ -44,6 +44,23 @@ struct Result {                          // published by the last CTA
     long long flagcnt[kFlagSlots];       // flagcnt[k] = 1 when status bit k is set (contiguous with limbs)
 };
 
+// Peer-memory mailbox for the fused limb exchange over NVLink / NVSwitch.  Rank r's last CTA stores
+// its 44 int64 (normalised limbs + status-flag counters) into slot [epoch & 1][r] of EVERY rank's
+// mailbox with plain peer stores, then publishes the epoch with a release store; each rank then
+// waits for all its slots of this epoch, sums them as integers, normalises and rounds -- inside the
+// reduction kernel, with no NCCL call and no extra launch.  Two slot sets suffice: a rank cannot
+// start epoch e+2 before every peer has finished reading epoch e (it needs their epoch e+1 data).
+constexpr int kMaxPeers = 8;
+constexpr int kMsgWords = kLimbs + kFlagSlots;   // 44
+struct MailSlot {
+    unsigned long long data[kMsgWords];
+    unsigned long long seq;
+    unsigned long long pad[3];                   // 48 words = 384 B per slot
+};
+struct Mailbox {
+    MailSlot slot[2][kMaxPeers];
+};
+
 struct ReduceParams {
     const double* a;                     // already offset by `offset`
     const double* b;                     // ExDOT only
@@ -58,6 +75,10 @@ struct ReduceParams {
     int keep;                            // 1: do not reset the accumulator after publishing
     int adaptive;                        // 1: bypass the expansion while it thrashes (performance only)
     int fresh;                           // 1: the workspace accumulator is known to be zero (no pending chunks)
+    // fused multi-GPU exchange (0 ranks = off): every rank's mailbox, mapped into this process
+    Mailbox* peers[kMaxPeers];
+    int nranks, rank;
+    unsigned long long epoch;            // identifies this collective reduction (same on every rank, >= 1)
 };
 
 EXB_D Vec4 ldg256(const double* p) {
@@ -66,6 +87,23 @@ EXB_D Vec4 ldg256(const double* p) {
                  : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
                  : "l"(p));
     return r;
+}
+
+EXB_D void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+EXB_D void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+EXB_D unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+EXB_D unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 
 EXB_D bool nonzero_bits(double x) {
@@ -521,11 +559,64 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
                 block_limbs[j] = (long long)atomicExch(&prm.ws->gacc[j], 0ull);
             __syncthreads();
         }
+        __shared__ unsigned final_status;
         if (tid == 0) {
             unsigned st;
             if (solo) st = block_status;
             else st = prm.finalize && !prm.keep ? atomicExch(&prm.ws->status, 0u) : atomicOr(&prm.ws->status, 0u);
-            const bool neg = normalize_shared(block_limbs);
+            normalize_shared(block_limbs);
+            final_status = st;
+        }
+        __syncthreads();
+        // ---- fused multi-GPU exchange over peer memory (only the closing launch of a reduction) ----
+        if (prm.finalize && prm.nranks > 1) {
+            const unsigned set = (unsigned)(prm.epoch & 1ull);
+            const unsigned st = final_status;
+            for (unsigned j = tid; j < (unsigned)kMsgWords * (unsigned)prm.nranks; j += T) {
+                const unsigned r = j / kMsgWords, w = j % kMsgWords;
+                const unsigned long long v = w < (unsigned)kLimbs ? (unsigned long long)block_limbs[w]
+                                                                  : (unsigned long long)((st >> (w - kLimbs)) & 1u);
+                st_relaxed_sys(&prm.peers[r]->slot[set][prm.rank].data[w], v);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < (unsigned)prm.nranks) st_release_sys(&prm.peers[tid]->slot[set][prm.rank].seq, prm.epoch);
+            // wait for every rank's contribution of this epoch in MY mailbox (bounded spin)
+            __shared__ unsigned timed_out;
+            if (tid == 0) timed_out = 0;
+            __syncthreads();
+            if (tid < (unsigned)prm.nranks) {
+                const unsigned long long* seq = &prm.peers[prm.rank]->slot[set][tid].seq;
+                const long long t0 = clock64();
+                while (ld_acquire_sys(seq) != prm.epoch) {
+                    if (clock64() - t0 > 20000000000ll) {        // ~10 s: a peer never arrived
+                        atomicOr(&timed_out, 1u);
+                        break;
+                    }
+                    __nanosleep(200);
+                }
+            }
+            __syncthreads();
+            __shared__ unsigned long long merged[kMsgWords];
+            for (unsigned w = tid; w < (unsigned)kMsgWords; w += T) {
+                unsigned long long sum = 0;
+                for (int r = 0; r < prm.nranks; ++r) sum += ld_relaxed_sys(&prm.peers[prm.rank]->slot[set][r].data[w]);
+                merged[w] = sum;                                 // <= 8 normalised limbs: no overflow
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned stm = timed_out ? kStPeerTimeout : 0u;
+                for (int k = 0; k < kFlagSlots; ++k)
+                    if (merged[kLimbs + k] != 0) stm |= 1u << k;
+                for (int j = 0; j < kLimbs; ++j) block_limbs[j] = (long long)merged[j];
+                normalize_shared(block_limbs);
+                final_status = stm;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const unsigned st = final_status;
+            const bool neg = block_limbs[kLimbs - 1] < 0;
             if (prm.finalize) {
                 Result* out = prm.out;
                 for (int j = 0; j < kLimbs; ++j) out->limbs[j] = block_limbs[j];

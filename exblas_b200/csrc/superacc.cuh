@@ -51,6 +51,7 @@ enum : unsigned {
     kStNegInf = 4u,      // -Inf met
     kStTooLarge = 8u,    // finite |x| >= 2^988: above the 39-limb layout; element dropped
     kStTooSmall = 16u,   // bits below 2^-1040 were truncated: result no longer exact
+    kStPeerTimeout = 32u,  // fused multi-GPU exchange: a peer's contribution never arrived (result is partial)
 };
 
 // Limb deposits between two boundings of one accumulator column (bound_column): each deposit adds a

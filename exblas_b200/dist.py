@@ -6,7 +6,10 @@ its shard to 39 normalised int64 limbs on its GPU, the ranks sum those limbs as 
 order-free), and every rank normalises and rounds the same integers -- so all ranks, and any
 number of ranks, return identical bits.
 
-Two transports for the 44 x int64 message (39 limbs + 5 status-flag counters):
+Three transports for the 44 x int64 message (39 limbs + 5 status-flag counters):
+  * `init_peer()`            -- FUSED: the closing reduction kernel stores the message into every
+    peer's mailbox over NVLink peer memory and merges what it receives, no collective call at all
+    (exblas_b200_peer_export / exblas_b200_peer_attach);
   * `Handle.allreduce_async` -- ncclAllReduce on the handle's own stream through the C ABI
     (exblas_b200_comm_init / exblas_b200_allreduce_async); used by bench.py and on GPUs;
   * `allreduce_limbs`        -- torch.distributed.all_reduce on a tensor, any backend (gloo in
@@ -100,6 +103,18 @@ class DistributedReducer:
         self.dist.broadcast_object_list(obj, src=0, group=self.group)
         self.handle.comm_init(self.world, self.rank, obj[0])
         self._nccl_ready = True
+
+    def init_peer(self) -> None:
+        """Set up the FUSED exchange: every rank exports its mailbox (CUDA IPC), the handles are gathered
+        in rank order, every rank maps its peers.  Afterwards each reduction exchanges its limbs inside
+        the closing kernel over NVLink peer memory; no NCCL call, no extra launch."""
+        if self.world == 1:
+            return
+        mine = self.handle.peer_export()
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, mine, group=self.group)
+        self.handle.peer_attach(self.world, self.rank, handles)
+        self.dist.barrier(group=self.group)      # nobody launches before every mailbox is mapped
 
     # device-resident shard in, identical value on every rank out
     def exsum(self, n_local: int, d_a, fpe: int = 0, early_exit: bool = False, round_mode: int = ROUND_REFERENCE):

@@ -52,6 +52,7 @@ extern "C" {
 #define EXBLAS_B200_ST_NEGINF 4u      /* -Inf met */
 #define EXBLAS_B200_ST_TOOLARGE 8u    /* finite |x| (or product) >= 2^988: outside the 39-limb layout, dropped */
 #define EXBLAS_B200_ST_TOOSMALL 16u   /* bits below 2^-1040 truncated: result not exact */
+#define EXBLAS_B200_ST_PEERTIMEOUT 32u /* fused multi-GPU exchange: a peer never arrived; result is partial */
 
 typedef struct exblas_b200_handle_s* exblas_b200_handle_t;
 
@@ -142,6 +143,17 @@ int exblas_b200_comm_init(exblas_b200_handle_t handle, int nranks, int rank, con
  * *_async call, then normalise and round on every rank: every rank ends with identical bits.
  * Replaces MPI_Reduce(MPI_LONG, MPI_SUM) + Round() of cpu ExSUM.cpp:266-273. */
 int exblas_b200_allreduce_async(exblas_b200_handle_t handle, int round_mode);
+
+/* Fused alternative to the NCCL path: the limb exchange happens INSIDE the closing reduction kernel
+ * over peer-mapped memory (NVLink / NVSwitch), no NCCL call and no extra launch.  Every rank calls
+ * peer_export (a 64-byte CUDA IPC handle of its mailbox), the 64-byte handles of all ranks are
+ * gathered in rank order by any means, and every rank calls peer_attach.  From then on every
+ * *_async reduction on this handle is a COLLECTIVE: all ranks must issue the same sequence of
+ * reductions; each ends with identical value / limbs / status on every rank, and
+ * exblas_b200_allreduce_async becomes a no-op.  Option "fused_allreduce" = 0 switches back to NCCL.
+ * One process per GPU, at most 8 ranks on one NVLink domain. */
+int exblas_b200_peer_export(exblas_b200_handle_t handle, void* handle64);
+int exblas_b200_peer_attach(exblas_b200_handle_t handle, int nranks, int rank, const void* handles);
 
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 int exblas_b200_last_status(exblas_b200_handle_t handle, uint32_t* status_flags);

@@ -45,9 +45,26 @@ def _worker(rank, world, port, n, q):
                 out.append(("sum", fpe, ee, rm, v, l.tolist(), st))
             v, l, st = red.exdot(hi - lo, x, y, fpe, ee, 1)
             out.append(("dot", fpe, ee, 1, v, l.tolist(), st))
-        # a rank-local special must reach every rank
+        # the FUSED transport (limb exchange inside the closing kernel over peer memory) must give the
+        # same bits as the NCCL transport, reduction after reduction (epochs alternate mailbox sets)
+        nccl_results = [(rec[4], rec[5], rec[6]) for rec in out]
+        red.init_peer()
+        fused = []
+        for rep in range(3):
+            for fpe, ee in [(0, False), (4, False), (8, True)]:
+                for rm in (0, 1):
+                    v, l, st = red.exsum(hi - lo, a, fpe, ee, rm)
+                    fused.append((v, l.tolist(), st))
+                v, l, st = red.exdot(hi - lo, x, y, fpe, ee, 1)
+                fused.append((v, l.tolist(), st))
+        assert fused == nccl_results * 3, "fused peer-memory exchange differs from the NCCL all-reduce"
+        out.append(("fused_ok", len(fused)))
+        # a rank-local special must reach every rank (fused transport, then NCCL again)
         if rank == world - 1:
             a[5] = float("inf")
+        v, l, st = red.exsum(hi - lo, a, 4, False, 0)
+        out.append(("inf", v, st))
+        h.set_option("fused_allreduce", 0)
         v, l, st = red.exsum(hi - lo, a, 4, False, 0)
         out.append(("inf", v, st))
         q.put((rank, out))
@@ -97,5 +114,7 @@ def test_sharded_equals_single_gpu(gpu):
                 assert v == w and l == wl.tolist() and st == wst == 0, (world, fpe, ee, rm)
             elif rec[0] == "dot":
                 assert rec[4] == 1.5 and rec[6] == 0, (world, rec[:4])
+            elif rec[0] == "fused_ok":
+                assert rec[1] == 27
             else:
                 assert rec[1] == float("inf") and rec[2] == 2
