@@ -250,8 +250,10 @@ def run_ours(args, fpes):
     if world > 1:
         red = xd.DistributedReducer(h)
         red.init_nccl()
-        if args.collective == "fused":
-            red.init_peer()
+        if args.collective == "fused" and not red.init_peer():
+            args.collective = "nccl (fused exchange unavailable: CUDA IPC mapping failed)"
+            if rank == 0:
+                print("bench: falling back to the NCCL limb all-reduce", file=sys.stderr)
 
     a = gen(args.dist, n_total, rank * n, (rank + 1) * n, 1, dev)
     b = gen(args.dist, n_total, rank * n, (rank + 1) * n, 2, dev) if args.op == "exdot" else None

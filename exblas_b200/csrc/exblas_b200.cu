@@ -774,10 +774,11 @@ int exblas_b200_comm_init(exblas_b200_handle_t h, int nranks, int rank, const vo
 int exblas_b200_peer_export(exblas_b200_handle_t h, void* handle64) {
     if (!h || !handle64) return EXBLAS_B200_EINVAL;
     CK(cudaSetDevice(h->device));
-    if (!h->d_mailbox) {
-        CK(cudaMalloc(&h->d_mailbox, sizeof(Mailbox)));
-        CK(cudaMemset(h->d_mailbox, 0, sizeof(Mailbox)));
-    }
+    if (!h->d_mailbox) CK(cudaMalloc(&h->d_mailbox, sizeof(Mailbox)));
+    // (re-)initialise: epochs restart at 1 after every attach, so no stale sequence number may survive
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemset(h->d_mailbox, 0, sizeof(Mailbox)));
+    CK(cudaDeviceSynchronize());
     cudaIpcMemHandle_t ipc;
     CK(cudaIpcGetMemHandle(&ipc, h->d_mailbox));
     static_assert(sizeof(ipc) == 64, "CUDA IPC handles are 64 bytes");

@@ -93,6 +93,7 @@ class DistributedReducer:
         self.world = dist.get_world_size(group)
         self.handle = handle
         self._nccl_ready = False
+        self.fused = False
 
     def init_nccl(self) -> None:
         """Create the C-ABI NCCL communicator: rank 0 makes the unique id, everyone gets it through
@@ -104,17 +105,32 @@ class DistributedReducer:
         self.handle.comm_init(self.world, self.rank, obj[0])
         self._nccl_ready = True
 
-    def init_peer(self) -> None:
+    def init_peer(self) -> bool:
         """Set up the FUSED exchange: every rank exports its mailbox (CUDA IPC), the handles are gathered
         in rank order, every rank maps its peers.  Afterwards each reduction exchanges its limbs inside
-        the closing kernel over NVLink peer memory; no NCCL call, no extra launch."""
+        the closing kernel over NVLink peer memory; no NCCL call, no extra launch.  Collective-safe:
+        returns False on EVERY rank (and leaves the handle on its previous transport) if any rank could
+        not export or map a mailbox, e.g. where CUDA IPC is not permitted."""
         if self.world == 1:
-            return
-        mine = self.handle.peer_export()
+            return True
+        try:
+            mine = self.handle.peer_export()
+        except Exception:
+            mine = None
         handles = [None] * self.world
         self.dist.all_gather_object(handles, mine, group=self.group)
-        self.handle.peer_attach(self.world, self.rank, handles)
-        self.dist.barrier(group=self.group)      # nobody launches before every mailbox is mapped
+        ok = all(hd is not None for hd in handles)
+        if ok:
+            try:
+                self.handle.peer_attach(self.world, self.rank, handles)
+            except Exception:
+                ok = False
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, ok, group=self.group)   # also: nobody launches before all are mapped
+        ok = all(flags)
+        self.handle.set_option("fused_allreduce", 1 if ok else 0)
+        self.fused = ok
+        return ok
 
     # device-resident shard in, identical value on every rank out
     def exsum(self, n_local: int, d_a, fpe: int = 0, early_exit: bool = False, round_mode: int = ROUND_REFERENCE):
