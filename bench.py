@@ -379,7 +379,8 @@ def run_ours(args, fpes):
                "h2d_bytes_per_step": n * bytes_per_elem * len(fpes), "d2h_bytes_per_step": 368 * len(fpes),
                "steps": e2e_steps, "ms_per_step": round(dt * 1e3, 2),
                "note": "exblas_b200_exsum/exdot (host pointers, pinned): chunked H2D overlapped with the kernels, "
-                       "result read back each call; per rank when N > 1 (host shards are not combined across ranks)",
+                       "result read back each call; N > 1: every rank streams its own host shard, and with the fused transport the "
+                       "closing kernel of each call also exchanges limbs with the peers",
                "matches_device_result": bool(v_e2e == results[fpes[-1]][0]) if world == 1 else None}
         del ha, hb
 
