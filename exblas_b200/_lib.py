@@ -39,6 +39,9 @@ SIGNATURES = {
     "exblas_b200_result_ptr": (C.c_int, [_h, C.POINTER(C.c_void_p)]),
     "exblas_b200_exgemv": (C.c_int, [_h, C.c_char, _i64, _i64, C.c_double, _dp, _i64, _i64, _dp, _i64, _i64, C.c_double,
                                      _dp, _i64, _i64, C.c_int, C.c_int, C.c_int]),
+    "exblas_b200_exsum_segments": (C.c_int, [_h, _dp, C.c_void_p, _i64, C.c_int, C.c_int, C.c_int, _dp, C.c_void_p]),
+    "exblas_b200_exdot_segments": (C.c_int, [_h, _dp, _dp, C.c_void_p, _i64, C.c_void_p, _i64, C.c_int, C.c_int, C.c_int, _dp,
+                                             C.c_void_p]),
     "exblas_b200_sync": (C.c_int, [_h]),
     "exblas_b200_round": (C.c_int, [C.POINTER(_i64), C.c_int, C.POINTER(C.c_double)]),
     "exblas_b200_merge_limbs": (C.c_int, [C.POINTER(_i64), C.POINTER(_i64)]),

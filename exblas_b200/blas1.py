@@ -96,6 +96,57 @@ class Handle:
         del ka, kb
         return (res.value, np.array(limbs, dtype=np.int64)) if want_limbs else res.value
 
+    # -- batched ("segmented") reductions: one launch, one warp per segment -------------------
+    def exsum_segments(self, a, seg, fpe=0, early_exit=False, round_mode=ROUND_REFERENCE, out=None, want_status=False):
+        """results[s] = exact sum of a[seg[s]:seg[s+1]], rounded.  a / seg / out: all numpy (host) or all
+        torch CUDA tensors (seg int64).  Returns out (allocated when None) [, per-segment status flags]."""
+        return self._segments(a, None, None, seg, fpe, early_exit, round_mode, out, want_status)
+
+    def exdot_segments(self, a, b, seg, gather=None, fpe=0, early_exit=False, round_mode=ROUND_REFERENCE, out=None,
+                       want_status=False):
+        """results[s] = exact sum of a[i] * b[gather[i] if gather is not None else i] over seg[s] <= i < seg[s+1].
+        With gather (int32 column indices) this is a CSR sparse matrix-vector product."""
+        return self._segments(a, b, gather, seg, fpe, early_exit, round_mode, out, want_status)
+
+    def _segments(self, a, b, gather, seg, fpe, early_exit, round_mode, out, want_status):
+        on_gpu = hasattr(a, "data_ptr")
+        if on_gpu:
+            import torch
+            if seg.dtype != torch.int64 or (gather is not None and gather.dtype != torch.int32):
+                raise TypeError("seg must be int64, gather int32")
+            nseg = seg.numel() - 1
+            if out is None:
+                out = torch.empty(max(nseg, 0), dtype=torch.float64, device=a.device)
+            st = torch.zeros(max(nseg, 0), dtype=torch.int32, device=a.device) if want_status else None
+            ptr = lambda t: t.data_ptr() if t is not None else None
+            nb = b.numel() if b is not None else 0
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            b = np.ascontiguousarray(b, dtype=np.float64) if b is not None else None
+            seg = np.ascontiguousarray(seg, dtype=np.int64)
+            gather = np.ascontiguousarray(gather, dtype=np.int32) if gather is not None else None
+            nseg = seg.size - 1
+            if nseg >= 0 and seg.size and int(seg[-1]) > a.size:
+                raise ValueError("seg reads past the end of a")
+            if b is not None and gather is None and nseg >= 0 and seg.size and int(seg[-1]) > b.size:
+                raise ValueError("seg reads past the end of b")
+            if out is None:
+                out = np.empty(max(nseg, 0), dtype=np.float64)
+            st = np.zeros(max(nseg, 0), dtype=np.uint32) if want_status else None
+            ptr = lambda t: t.ctypes.data if t is not None else None
+            nb = b.size if b is not None else 0
+        if nseg < 0:
+            raise ValueError("seg needs at least one offset")
+        if b is None:
+            check(self.lib.exblas_b200_exsum_segments(self._h, ptr(a), ptr(seg), nseg, fpe, int(early_exit), round_mode,
+                                                      ptr(out), ptr(st)), self._h)
+        else:
+            check(self.lib.exblas_b200_exdot_segments(self._h, ptr(a), ptr(b), ptr(gather), nb, ptr(seg), nseg, fpe,
+                                                      int(early_exit), round_mode, ptr(out), ptr(st)), self._h)
+        if on_gpu:
+            check(self.lib.exblas_b200_sync(self._h), self._h)
+        return (out, st) if want_status else out
+
     # -- asynchronous, device-resident ---------------------------------------------------------
     def exsum_async(self, Ng, d_ag, inca=1, offset=0, fpe=0, early_exit=False, round_mode=ROUND_REFERENCE):
         addr, size, _ = _address(d_ag)

@@ -23,6 +23,7 @@
 #include "../../include/exblas_b200.h"
 #include "reduce_kernel.cuh"
 #include "gemv_kernel.cuh"
+#include "segments_kernel.cuh"
 
 using namespace exb;
 
@@ -107,6 +108,8 @@ struct exblas_b200_handle_s {
     int64_t opt_host_chunk = (int64_t)1 << 23;
     int64_t opt_adaptive = 1;
     int64_t opt_gemv_parts = 0;
+    int64_t opt_gemv_t_shape = 0;
+    int64_t opt_window = 1;                 // register window in the superaccumulator-only kernels (performance only)
     void* comm = nullptr;
     int nranks = 1;
     // fused peer-memory exchange (exblas_b200_peer_export / peer_attach)
@@ -131,7 +134,13 @@ cudaError_t allow_big_smem(const void* fn, int device) {
     const uint64_t key = (uint64_t)(uintptr_t)fn * 131u + (uint64_t)device;
     std::lock_guard<std::mutex> lock(mu);
     if (done.count(key)) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * kLimbs * (int)sizeof(long long));
+    // the opt-in limit (227 KB on sm_100) covers static + dynamic shared memory together
+    cudaFuncAttributes attr;
+    cudaError_t e = cudaFuncGetAttributes(&attr, fn);
+    if (e != cudaSuccess) return e;
+    int optin = 227 * 1024;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)attr.sharedSizeBytes);
     if (e == cudaSuccess) done.insert(key);
     return e;
 }
@@ -373,6 +382,7 @@ typedef void (*gemv_fn)(const GemvParams);
 // a deep window of 8-byte loads, the expansion), which a 512-thread CTA cannot have without spills.
 constexpr int kGemvT = 384;
 constexpr int gemv_groups_in_flight(int f) { return f <= 4 ? 4 : 3; }
+constexpr int kGemvWinU = 8;        // column groups in flight per thread in the register-window kernel
 
 template <int F, bool EE, bool A1>
 gemv_fn gemv_ptr() {
@@ -401,11 +411,12 @@ gemv_fn select_gemv(int f, bool ee) {
 }
 
 // Column split: enough CTAs to fill every SM for whole waves, as little limb scratch as possible.
-int choose_gemv_parts(int64_t row_blocks, int64_t n, int num_sms) {
-    int best = 1;
+int choose_gemv_parts(int64_t row_blocks, int64_t n, int num_sms, int pmin = 1) {
+    int best = pmin;
     double best_cost = 1e300;
-    const int64_t pmax = n / 64 > 0 ? (n / 64 < 64 ? n / 64 : 64) : 1;
-    for (int p = 1; p <= pmax; ++p) {
+    int64_t pmax = n / 64 > 0 ? (n / 64 < 64 ? n / 64 : 64) : 1;
+    if (pmax < pmin) pmax = pmin;
+    for (int p = pmin; p <= pmax; ++p) {
         const double ctas = (double)row_blocks * p;
         const double waves = ceil(ctas / num_sms);
         const double eff = ctas / (waves * num_sms);
@@ -419,22 +430,58 @@ int choose_gemv_parts(int64_t row_blocks, int64_t n, int num_sms) {
 }
 
 int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, const double* a, int64_t rs, int64_t cs,
-                const double* x, int64_t incx, double beta, double* y, int64_t incy, int f, bool ee, int round_mode) {
+                const double* x, int64_t incx, double beta, double* y, int64_t incy, int f, bool ee, int round_mode,
+                bool transposed) {
+    // 'T' with alpha == 1 and columns long enough to amortise the per-output warp merge: one warp per
+    // output, register windows, no scratch and no second kernel (exgemv_t_win_kernel).  Every fpe value
+    // takes it -- fpe only selects HOW the exact sum is accumulated, never the result.
+    if (transposed && alpha == 1.0 && h->opt_window && n >= 256) {
+        GemvParams p;
+        memset(&p, 0, sizeof(p));
+        p.a = a;
+        p.x = x;
+        p.y = y;
+        p.m = m;
+        p.n = n;
+        p.rs = rs;
+        p.cs = cs;
+        p.incx = incx;
+        p.incy = incy;
+        p.alpha = alpha;
+        p.beta = beta;
+        p.ws = h->d_ws;
+        p.round_mode = round_mode;
+        // two shapes (option "gemv_t_shape"): 0 = 256 threads x 8 groups in flight (no register spills),
+        // 1 = 384 threads x 6 groups
+        const bool wide = h->opt_gemv_t_shape == 1;
+        const int T = wide ? 384 : 256, nwarps = T / 32, chunk = wide ? 6144 : 8192;
+        const int64_t nsets = (m + nwarps - 1) / nwarps;
+        const unsigned grid = (unsigned)(nsets < h->num_sms ? nsets : h->num_sms);
+        const size_t smem = ((size_t)T * kLimbs + 2 * (size_t)chunk + 40 * (size_t)nwarps) * sizeof(long long);
+        gemv_fn fn = wide ? exgemv_t_win_kernel<6, 384, 6144> : exgemv_t_win_kernel<8, 256, 8192>;
+        CK(allow_big_smem((const void*)fn, h->device));
+        void* args[] = {(void*)&p};
+        CK(cudaLaunchKernel((const void*)fn, dim3(grid), dim3((unsigned)T), args, smem, h->stream));
+        h->launches += 1;
+        return EXBLAS_B200_OK;
+    }
     int T = kGemvT;
     if (m < T) T = (int)((m + 31) / 32 * 32);
     if (T < 32) T = 32;
     const int64_t row_blocks = (m + T - 1) / T;
-    int parts = h->opt_gemv_parts > 0 ? (int)h->opt_gemv_parts : choose_gemv_parts(row_blocks, n, h->num_sms);
+    // superaccumulator-only mode, alpha == 1, unit row stride: the register-window kernel (window.cuh);
+    // it stages its slice of x in shared memory, so a part holds at most kGemvXsMax columns
+    const bool windowed = f == 0 && alpha == 1.0 && rs == 1 && h->opt_window;
+    const int pmin = windowed ? (int)((n + kGemvXsMax - 1) / kGemvXsMax) : 1;
+    int parts = h->opt_gemv_parts > 0 ? (int)h->opt_gemv_parts : choose_gemv_parts(row_blocks, n, h->num_sms, pmin > 0 ? pmin : 1);
+    if (parts < pmin) parts = pmin;
     int64_t cpp = ((n + parts - 1) / parts + 3) / 4 * 4;
     if (cpp < 4) cpp = 4;
     parts = (int)((n + cpp - 1) / cpp);
     if (parts < 1) parts = 1;
     const size_t need = (size_t)parts * m * (kLimbs * sizeof(long long) + sizeof(unsigned));
     if (need > h->gemv_scratch_bytes) {
-        for (int r = 0; r < h->peer_ranks; ++r)
-        if (h->peer_box[r] && h->peer_box[r] != h->d_mailbox) cudaIpcCloseMemHandle(h->peer_box[r]);
-    if (h->d_mailbox) cudaFree(h->d_mailbox);
-    if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
+        if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
         h->d_gemv_scratch = nullptr;
         h->gemv_scratch_bytes = 0;
         CK(cudaMalloc(&h->d_gemv_scratch, need));
@@ -461,8 +508,10 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     p.round_mode = round_mode;
     p.adaptive = h->opt_adaptive ? 1 : 0;
     p.x_vec_ok = (incx == 1 && ((uintptr_t)x % 32) == 0) ? 1 : 0;       // part starts are multiples of 4 columns
-    gemv_fn fn = alpha == 1.0 ? select_gemv<true>(f, ee) : select_gemv<false>(f, ee);
-    const size_t smem = (size_t)T * kLimbs * sizeof(long long);
+    gemv_fn fn = windowed ? exgemv_n_win_kernel<kGemvWinU, kGemvT>
+                          : (alpha == 1.0 ? select_gemv<true>(f, ee) : select_gemv<false>(f, ee));
+    const size_t smem = windowed ? (size_t)kGemvT * kLimbs * sizeof(long long) + (size_t)cpp * sizeof(double)   // fixed limb stride
+                                 : (size_t)T * kLimbs * sizeof(long long);
     CK(allow_big_smem((const void*)fn, h->device));
     void* args[] = {(void*)&p};
     CK(cudaLaunchKernel((const void*)fn, dim3((unsigned)row_blocks, (unsigned)parts), dim3((unsigned)T), args, smem,
@@ -470,6 +519,112 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     exgemv_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(p);
     CK(cudaGetLastError());
     h->launches += 2;
+    return EXBLAS_B200_OK;
+}
+
+// Batched reductions: one warp per segment (segments_kernel.cuh).  All pointers are device pointers.
+typedef void (*seg_fn)(const SegParams);
+constexpr int kSegT = 256;
+
+int segments_device(exblas_b200_handle_t h, const double* a, const double* b, const int* gather, const int64_t* seg,
+                    int64_t nseg, int round_mode, double* results, uint32_t* statuses) {
+    SegParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = a;
+    p.b = b;
+    p.gather = gather;
+    p.seg = (const long long*)seg;
+    p.nseg = nseg;
+    p.results = results;
+    p.statuses = statuses;
+    p.ws = h->d_ws;
+    p.round_mode = round_mode;
+    seg_fn fn = b ? (gather ? exblas_segments_kernel<true, true, kSegT> : exblas_segments_kernel<true, false, kSegT>)
+                  : exblas_segments_kernel<false, false, kSegT>;
+    const int nwarps = kSegT / 32;
+    const size_t smem = ((size_t)kSegT * kLimbs + 40 * (size_t)nwarps) * sizeof(long long);
+    int64_t grid = (nseg + nwarps - 1) / nwarps;
+    if (grid > 2 * (int64_t)h->num_sms) grid = 2 * (int64_t)h->num_sms;
+    CK(allow_big_smem((const void*)fn, h->device));
+    void* args[] = {(void*)&p};
+    CK(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3((unsigned)kSegT), args, smem, h->stream));
+    h->launches += 1;
+    return EXBLAS_B200_OK;
+}
+
+int segments_any(exblas_b200_handle_t h, const double* a, const double* b, const int32_t* gather, int64_t nb,
+                 const int64_t* seg, int64_t nseg, int round_mode, double* results, uint32_t* statuses) {
+    if (!h) return EXBLAS_B200_EINVAL;
+    if (nseg < 0 || (nseg > 0 && (!seg || !results)) || (gather && !b)) {
+        h->err = "segments: invalid argument";
+        return EXBLAS_B200_EINVAL;
+    }
+    if (nseg == 0) return EXBLAS_B200_OK;
+    CK(cudaSetDevice(h->device));
+    const bool dev = is_device_pointer(results);
+    if (dev) {
+        int rc = segments_device(h, a, b, (const int*)gather, seg, nseg, round_mode, results, statuses);
+        if (rc) return rc;
+    } else {
+        // host operands (what the reference's callers hold): validate the offsets, stage everything once
+        int64_t total = 0;
+        for (int64_t s = 0; s < nseg; ++s) {
+            if (seg[s] < 0 || seg[s + 1] < seg[s]) {
+                h->err = "segments: offsets must be non-negative and non-decreasing";
+                return EXBLAS_B200_EINVAL;
+            }
+        }
+        total = seg[nseg];
+        if (total > 0 && (!a || ((b != nullptr) && !gather && !b))) return EXBLAS_B200_EINVAL;
+        if (gather) {
+            if (nb <= 0) {
+                h->err = "segments: nb (length of b) is required with a gather index on host operands";
+                return EXBLAS_B200_EINVAL;
+            }
+            for (int64_t i = seg[0]; i < total; ++i)
+                if (gather[i] < 0 || gather[i] >= nb) {
+                    h->err = "segments: gather index out of range";
+                    return EXBLAS_B200_EINVAL;
+                }
+        }
+        double *da = nullptr, *db = nullptr, *dr = nullptr;
+        int* dg = nullptr;
+        int64_t* ds = nullptr;
+        uint32_t* dst = nullptr;
+        const size_t nbv = b ? (gather ? (size_t)nb : (size_t)total) : 0;
+        int rc = [&]() -> int {
+            if (total) CK(cudaMalloc(&da, (size_t)total * sizeof(double)));
+            if (nbv) CK(cudaMalloc(&db, nbv * sizeof(double)));
+            if (gather && total) CK(cudaMalloc(&dg, (size_t)total * sizeof(int)));
+            CK(cudaMalloc(&ds, (size_t)(nseg + 1) * sizeof(int64_t)));
+            CK(cudaMalloc(&dr, (size_t)nseg * sizeof(double)));
+            CK(cudaMalloc(&dst, (size_t)nseg * sizeof(uint32_t)));
+            if (total) CK(cudaMemcpyAsync(da, a, (size_t)total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            if (nbv) CK(cudaMemcpyAsync(db, b, nbv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            if (dg) CK(cudaMemcpyAsync(dg, gather, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(ds, seg, (size_t)(nseg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+            int r2 = segments_device(h, da, b ? db : nullptr, dg, ds, nseg, round_mode, dr, dst);
+            if (r2) return r2;
+            CK(cudaMemcpyAsync(results, dr, (size_t)nseg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            if (statuses) CK(cudaMemcpyAsync(statuses, dst, (size_t)nseg * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            return EXBLAS_B200_OK;
+        }();
+        if (da) cudaFree(da);
+        if (db) cudaFree(db);
+        if (dg) cudaFree(dg);
+        if (ds) cudaFree(ds);
+        if (dr) cudaFree(dr);
+        if (dst) cudaFree(dst);
+        if (rc) return rc;
+    }
+    // status word (OR over all segments): read and reset, stream ordered
+    CK(cudaMemcpyAsync(&h->h_res->status, &h->d_ws->status, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemsetAsync(&h->d_ws->status, 0, sizeof(unsigned), h->stream));
+    if (!dev) {
+        CK(cudaStreamSynchronize(h->stream));
+        h->last_status = h->h_res->status;
+    }
     return EXBLAS_B200_OK;
 }
 
@@ -580,6 +735,11 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "gemv_parts")) {
         if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;
         h->opt_gemv_parts = value;
+    } else if (!strcmp(name, "gemv_t_shape")) {
+        if (value < 0 || value > 1) return EXBLAS_B200_EINVAL;
+        h->opt_gemv_t_shape = value;
+    } else if (!strcmp(name, "window")) {
+        h->opt_window = value != 0;
     } else if (!strcmp(name, "adaptive")) {
         h->opt_adaptive = value != 0;
     } else if (!strcmp(name, "host_chunk_elems")) {
@@ -642,6 +802,21 @@ int exblas_b200_exdot(exblas_b200_handle_t h, const double* a, int64_t inca, int
                                    result);
 }
 
+int exblas_b200_exsum_segments(exblas_b200_handle_t h, const double* a, const int64_t* seg, int64_t nseg, int fpe,
+                               int early_exit, int round_mode, double* results, uint32_t* statuses) {
+    if (fpe < 0) return EXBLAS_B200_EINVAL;
+    (void)early_exit;                      // every segment runs the superaccumulator + register window; fpe never changes a result
+    return segments_any(h, a, nullptr, nullptr, 0, seg, nseg, round_mode, results, statuses);
+}
+
+int exblas_b200_exdot_segments(exblas_b200_handle_t h, const double* a, const double* b, const int32_t* gather, int64_t nb,
+                               const int64_t* seg, int64_t nseg, int fpe, int early_exit, int round_mode, double* results,
+                               uint32_t* statuses) {
+    if (fpe < 0 || !b) return EXBLAS_B200_EINVAL;
+    (void)early_exit;
+    return segments_any(h, a, b, gather, nb, seg, nseg, round_mode, results, statuses);
+}
+
 int exblas_b200_exgemv(exblas_b200_handle_t h, char trans, int64_t m, int64_t n, double alpha, const double* a,
                        int64_t lda, int64_t offseta, const double* x, int64_t incx, int64_t offsetx, double beta,
                        double* y, int64_t incy, int64_t offsety, int fpe, int early_exit, int round_mode) {
@@ -670,7 +845,7 @@ int exblas_b200_exgemv(exblas_b200_handle_t h, char trans, int64_t m, int64_t n,
     const bool dev = is_device_pointer(py) && (ni == 0 || m == 0 || n == 0 || (is_device_pointer(pa) && is_device_pointer(px)));
     int rc;
     if (dev) {
-        rc = gemv_device(h, mo, ni, alpha, pa, rs, cs, px, incx, beta, py, incy, f, ee, round_mode);
+        rc = gemv_device(h, mo, ni, alpha, pa, rs, cs, px, incx, beta, py, incy, f, ee, round_mode, tr);
         if (rc) return rc;
     } else {
         // host operands (what the reference's exgemv takes, ExGEMV.cpp:109-234): stage on the device
@@ -684,7 +859,7 @@ int exblas_b200_exgemv(exblas_b200_handle_t h, char trans, int64_t m, int64_t n,
             if (na) CK(cudaMemcpyAsync(da, pa, na * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             if (nx) CK(cudaMemcpyAsync(dx, px, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(dy, py, ny * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            int r2 = gemv_device(h, mo, ni, alpha, da, rs, cs, dx, incx, beta, dy, incy, f, ee, round_mode);
+            int r2 = gemv_device(h, mo, ni, alpha, da, rs, cs, dx, incx, beta, dy, incy, f, ee, round_mode, tr);
             if (r2) return r2;
             CK(cudaMemcpyAsync(py, dy, ny * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));

@@ -22,6 +22,7 @@
 //   * beta*y is added exactly (TwoProd) as ExGEMV.FPE.cl:346-377 does, for any beta.
 #pragma once
 #include "reduce_kernel.cuh"
+#include "window.cuh"
 
 namespace exb {
 
@@ -212,6 +213,415 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
     if (valid) {
         long long* out = prm.scratch + (long long)blockIdx.y * kLimbs * prm.m + row_raw;
         for (int j = 0; j < kLimbs; ++j) out[(long long)j * prm.m] = (long long)lds64(col + j * stride);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ExGEMV 'N', superaccumulator-only mode (fpe < 2, alpha == 1) with a register window (window.cuh).
+//
+// Same decomposition as exgemv_n_kernel (thread per row, column split over blockIdx.y, per-part
+// limbs to scratch), but:
+//   * the CTA's slice of x is staged ONCE in shared memory behind the accumulator columns and read
+//     back with broadcast LDS.128 (no per-thread x registers in the load window, no L1 traffic);
+//   * A runs U column groups (4 columns each) ahead: 32 8-byte loads in flight per thread,
+//     ~96 KB per SM;
+//   * a group whose four products lie inside the window of EVERY lane of the warp (one vote) is
+//     accumulated in registers: 2 + 8 FP64 and 8 integer instructions per element, no shared-memory
+//     traffic.  Any other group takes the ordinary path (mul_add4<0>: TwoProd + two deposits per
+//     element) out of line, and lanes that keep missing re-anchor their window there;
+//   * a warp whose groups mostly miss (wide-range rows) stops voting for a while (exponential
+//     back-off), so such data costs what it cost before.
+// The result is the exact row sum whichever path each element took.
+// ------------------------------------------------------------------------------------------------
+EXB_D void lds128(unsigned addr, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+
+// Ordinary path for one group of four columns + window bookkeeping (rare: out of line, by value so
+// that the window stays in registers in the hot loop).
+__device__ __noinline__ Window gemv_slow_group(Window w, unsigned col, unsigned stride, double a0, double a1, double a2,
+                                               double a3, double x0, double x1, double x2, double x3, bool mine,
+                                               bool track) {
+    const double xa[4] = {a0, a1, a2, a3}, xb[4] = {x0, x1, x2, x3};
+    double none[1][expansions(0)];
+    unsigned status = w.st;
+    mul_add4<0, false, false>(col, stride, none, status, xa, xb);
+    if (track) {
+        unsigned hi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hi[k] = (unsigned)__double2hiint(__dmul_rn(xa[k], xb[k]));
+        win_after_slow_group<4>(w, mine, hi, false, [&](double v) { deposit(col, stride, v, status); });
+    }
+    w.st = status;
+    return w;
+}
+
+__device__ __noinline__ Window win_flush_products(Window w, unsigned col, unsigned stride) {
+    double out[4];
+    win_drain(w, out);
+    unsigned status = w.st;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (out[k] != 0.0) deposit(col, stride, out[k], status);
+    w.st = status;
+    return w;
+}
+
+constexpr int kGemvXsMax = 8192;          // doubles of x staged per CTA (64 KB)
+
+template <int U, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams prm) {
+    extern __shared__ long long smem[];
+    const unsigned T = blockDim.x;                           // <= MAXT
+    const unsigned tid = threadIdx.x;
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    constexpr unsigned stride = 8u * MAXT;                   // compile-time limb stride: column addresses are immediates
+    const unsigned col = smem_base + 8u * tid;
+#pragma unroll
+    for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+
+    const long long row_raw = (long long)blockIdx.x * T + tid;
+    const bool valid = row_raw < prm.m;
+    const long long row = valid ? row_raw : prm.m - 1;       // idle lanes redo the last row (keeps votes uniform)
+    const long long c0 = (long long)blockIdx.y * prm.cols_per_part;
+    long long c1 = c0 + prm.cols_per_part;
+    if (c1 > prm.n) c1 = prm.n;
+    const int ncols = (int)(c1 > c0 ? c1 - c0 : 0);          // <= kGemvXsMax
+    const int ngroups = ncols / 4;
+
+    // stage x[c0 .. c1) behind the columns
+    double* xs = reinterpret_cast<double*>(smem + (size_t)kLimbs * MAXT);
+    const unsigned xs_base = smem_base + stride * (unsigned)kLimbs;
+    for (int k = (int)tid; k < ncols; k += (int)T) xs[k] = prm.x[prm.incx * (c0 + k)];
+    __syncthreads();
+
+    Window w;
+    win_reset(w);
+    const long long cs = prm.cs;
+    const double* qa = prm.a + row * prm.rs + cs * c0;       // next group of A to load
+    const long long astep = 4 * cs;
+    double va[U][4];
+    auto load_group = [&](int u) {
+        va[u][0] = ldg64(qa);
+        va[u][1] = ldg64(qa + cs);
+        va[u][2] = ldg64(qa + 2 * cs);
+        va[u][3] = ldg64(qa + 3 * cs);
+        qa += astep;
+    };
+    const int rounds = ngroups / U;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (rounds > 0) load_group(u);
+
+    unsigned xaddr = xs_base;                                // x of the group being consumed
+    int since_norm = 0;
+    int r = 0;
+    // ---- loop 1: register window.  Two rounds in a row that mostly miss (wide-range rows) end it. ----
+    for (int bad = 0; r < rounds && bad < 2; ++r) {
+        const bool has_next = r + 1 < rounds;
+        int missed = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
+            if (has_next) load_group(u);
+            double x0, x1, x2, x3;
+            lds128(xaddr, x0, x1);
+            lds128(xaddr + 16u, x2, x3);
+            xaddr += 32u;
+            const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
+            const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
+            const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
+            const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
+            const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
+            const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+            if (__all_sync(0xffffffffu, mine)) {
+                win_add_product(w, p0, __fma_rn(a0, x0, -p0));
+                win_add_product(w, p1, __fma_rn(a1, x1, -p1));
+                win_add_product(w, p2, __fma_rn(a2, x2, -p2));
+                win_add_product(w, p3, __fma_rn(a3, x3, -p3));
+                w.cnt += 4u;
+            } else {
+                w = gemv_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
+                ++missed;
+            }
+        }
+        bad = (2 * missed > U) ? bad + 1 : 0;                // warp-uniform (the votes are)
+        if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) {
+            w = win_flush_products(w, col, stride);
+            since_norm += 4;
+        }
+        since_norm += missed * 12;                           // <= 8 deposits + a 4-deposit drain per slow group
+        if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
+            bound_column(col, stride);
+            since_norm = 0;
+        }
+    }
+    // ---- loop 2 (only after loop 1 gave up): every product takes the ordinary path, inlined ----
+    if (r < rounds) {
+        w = win_flush_products(w, col, stride);
+        since_norm += 4;
+        unsigned status = w.st;
+        for (; r < rounds; ++r) {
+            const bool has_next = r + 1 < rounds;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
+                if (has_next) load_group(u);
+                double xb[4];
+                lds128(xaddr, xb[0], xb[1]);
+                lds128(xaddr + 16u, xb[2], xb[3]);
+                xaddr += 32u;
+                double none[1][expansions(0)];
+                mul_add4<0, false, true>(col, stride, none, status, xa, xb);
+            }
+            since_norm += 8 * U;
+            if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
+                bound_column(col, stride);
+                since_norm = 0;
+            }
+        }
+        w.st = status;
+    }
+    // groups left over after the full rounds (< U of them), then columns left over (< 4): ordinary path
+    {
+        const double* ra = prm.a + row * prm.rs + cs * (c0 + (long long)rounds * U * 4);
+        for (int g = rounds * U; g < ngroups; ++g, ra += astep) {
+            const double* xg = xs + 4 * g;
+            w = gemv_slow_group(w, col, stride, ra[0], ra[cs], ra[2 * cs], ra[3 * cs], xg[0], xg[1], xg[2], xg[3], true,
+                                false);
+        }
+        unsigned status = w.st;
+        double none[1][expansions(0)];
+        for (int c = ngroups * 4; c < ncols; ++c, ra += cs) mul_add1<0, false>(col, stride, none, status, ra[0], xs[c]);
+        w.st = status;
+    }
+    w = win_flush_products(w, col, stride);
+    bound_column(col, stride);
+    const unsigned status = w.st;
+    if (status && valid) atomicOr(&prm.ws->status, status);
+    if (valid) prm.row_status[(long long)blockIdx.y * prm.m + row_raw] = status;
+    if (valid) {
+        long long* out = prm.scratch + (long long)blockIdx.y * kLimbs * prm.m + row_raw;
+        for (int j = 0; j < kLimbs; ++j) out[(long long)j * prm.m] = (long long)lds64(col + j * stride);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ExGEMV 'T' (y_j = alpha * sum_i A[i + j*lda] * x[i] + beta * y_j), alpha == 1, any fpe: one WARP per
+// output.  Column j of A is contiguous, so lane l streams rows l, l+32, l+64, ... with coalesced
+// 8-byte loads (256 B per warp instruction, no alignment requirement), U groups of 4 rows ahead.
+// All warps of the CTA walk the same rows of their respective columns, so x is staged once per CTA
+// in 2048-row chunks (cp.async, double buffered, one barrier per chunk) and read back with
+// conflict-free LDS.64.  Each lane accumulates in its register window (window.cuh) and, for what
+// falls outside, its private shared-memory column; at the end of the column the warp drains the
+// windows, sums the 32 columns limb by limb with shuffles (limbs that are zero in every lane are
+// skipped after one vote), and lane 0 adds beta*y exactly, rounds and stores y_j -- no scratch, no
+// second kernel.  Replaces the reference's gemvT kernels (ExGEMV.FPE.cl:382-557,
+// ExGEMV.Superacc.cl:295-395), whose threads walk a row of the transposed matrix with stride lda.
+// ------------------------------------------------------------------------------------------------
+EXB_D void cp_async8(unsigned dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+EXB_D void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+EXB_D double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+#ifndef EXB_TCHUNK
+#define EXB_TCHUNK 2048
+#endif
+// End of a column in exgemv_t_win_kernel (lane 0): summed limbs + beta*y -> rounded y.  Out of line:
+// it needs the 39 limbs in local memory and must not weigh on the streaming loop's registers.
+__device__ __noinline__ void gemv_t_store(const long long* wl, unsigned st, double* yp, double beta, int round_mode,
+                                          unsigned* ws_status) {
+    long long acc[kLimbs];
+    for (int jl = 0; jl < kLimbs; ++jl) acc[jl] = wl[jl];
+    if (beta != 0.0) {
+        const double yv = *yp;
+        if (beta == 1.0) {
+            st |= accumulate_double(acc, yv);
+        } else {
+            const double p = __dmul_rn(beta, yv);
+            const double e = __fma_rn(beta, yv, -p);
+            st |= accumulate_double(acc, p);
+            if (!(e != e)) st |= accumulate_double(acc, e);
+        }
+    }
+    *yp = finalize_value(acc, st, round_mode);
+    if (st) atomicOr(ws_status, st);
+}
+
+constexpr int kGemvTChunk = EXB_TCHUNK;   // rows of x staged per buffer
+
+template <int U, int MAXT, int kGemvTChunk>
+__global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams prm) {
+    // here prm.m = number of outputs (columns of A), prm.n = rows summed per output, prm.rs = lda, prm.cs = 1
+    extern __shared__ long long smem[];
+    const unsigned T = blockDim.x;                                                   // <= MAXT
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = T >> 5;
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    constexpr unsigned stride = 8u * MAXT;                                           // compile-time limb stride
+    const unsigned col = smem_base + 8u * tid;
+#pragma unroll
+    for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+    const unsigned xs_base = smem_base + stride * (unsigned)kLimbs;                  // 2 x kGemvTChunk doubles
+    long long* wl = smem + (size_t)kLimbs * MAXT + 2 * kGemvTChunk + (size_t)warp * 40;   // this warp's 39 summed limbs
+
+    const long long nrows = prm.n, nout = prm.m;
+    const long long nsets = (nout + nwarps - 1) / nwarps;
+    const int nchunks = (int)((nrows + kGemvTChunk - 1) / kGemvTChunk);
+    const long long full_groups = nrows / 128;                                       // groups of 4 rows per lane, all rows valid
+
+    auto stage = [&](int chunk) {                                                    // x[chunk] -> buffer chunk & 1 (zero padded)
+        const unsigned dst0 = xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u);
+        const long long r0 = (long long)chunk * kGemvTChunk;
+        for (int k = (int)tid; k < kGemvTChunk; k += (int)T) {
+            const long long r = r0 + k;
+            if (r < nrows) cp_async8(dst0 + 8u * (unsigned)k, prm.x + prm.incx * r);
+            else sts64(dst0 + 8u * (unsigned)k, 0ull);
+        }
+    };
+
+    Window w;
+    win_reset(w);
+    int skip_window = 0;                                                             // columns left to run without the window
+    for (long long set = blockIdx.x; set < nsets; set += gridDim.x) {
+        const long long jraw = set * nwarps + warp;
+        const bool valid = jraw < nout;
+        const long long j = valid ? jraw : nout - 1;                                 // spare warps redo the last column (they must meet the barriers)
+        const double* colp = prm.a + j * prm.rs + lane;                              // row `lane` of column j
+        const double* qa = colp;
+        double va[U][4];
+        auto load_group = [&](int u) {
+            va[u][0] = ldg64(qa);
+            va[u][1] = ldg64(qa + 32);
+            va[u][2] = ldg64(qa + 64);
+            va[u][3] = ldg64(qa + 96);
+            qa += 128;
+        };
+        const long long rounds = full_groups / U;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (rounds > 0) load_group(u);
+        __syncthreads();                                                             // previous set's readers of both x buffers are done
+        stage(0);
+        int since_norm = 0;
+        constexpr int RPC = kGemvTChunk / (128 * U);                                 // rounds per chunk of x
+        static_assert(RPC * 128 * U == kGemvTChunk, "a chunk of x must hold whole rounds");
+        auto chunk_gate = [&](long long r) -> unsigned {                             // returns the shared address of this lane's x for round r
+            const int chunk = (int)(r / RPC);
+            if (r % RPC == 0) {
+                cp_async_wait_all();
+                __syncthreads();                                                     // chunk resident; buffer (chunk + 1) & 1 is free
+                if (chunk + 1 < nchunks) stage(chunk + 1);
+            }
+            return xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u) + (unsigned)(r % RPC) * (128u * U * 8u) + 8u * lane;
+        };
+        long long r = 0;
+        // ---- loop 1: register window; two rounds in a row that mostly miss end it (for this and the next 7 columns) ----
+        if (skip_window > 0) --skip_window;
+        else for (int bad = 0; r < rounds && bad < 2; ++r) {
+            unsigned xaddr = chunk_gate(r);
+            const bool has_next = r + 1 < rounds;
+            int missed = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
+                if (has_next) load_group(u);
+                const double x0 = lds_f64(xaddr), x1 = lds_f64(xaddr + 256u), x2 = lds_f64(xaddr + 512u), x3 = lds_f64(xaddr + 768u);
+                xaddr += 1024u;
+                const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
+                const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
+                const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
+                const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
+                const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
+                const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+                if (__all_sync(0xffffffffu, mine)) {
+                    win_add_product(w, p0, __fma_rn(a0, x0, -p0));
+                    win_add_product(w, p1, __fma_rn(a1, x1, -p1));
+                    win_add_product(w, p2, __fma_rn(a2, x2, -p2));
+                    win_add_product(w, p3, __fma_rn(a3, x3, -p3));
+                    w.cnt += 4u;
+                } else {
+                    w = gemv_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
+                    ++missed;
+                }
+            }
+            bad = (2 * missed > U) ? bad + 1 : 0;
+            if (bad >= 2) skip_window = 7;
+            if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) {
+                w = win_flush_products(w, col, stride);
+                since_norm += 4;
+            }
+            since_norm += missed * 12;
+            if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
+                bound_column(col, stride);
+                since_norm = 0;
+            }
+        }
+        // ---- loop 2: wide-range column, every product takes the ordinary path, inlined ----
+        if (r < rounds) {
+            unsigned status = w.st;
+            for (; r < rounds; ++r) {
+                unsigned xaddr = chunk_gate(r);
+                const bool has_next = r + 1 < rounds;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
+                    if (has_next) load_group(u);
+                    const double xb[4] = {lds_f64(xaddr), lds_f64(xaddr + 256u), lds_f64(xaddr + 512u), lds_f64(xaddr + 768u)};
+                    xaddr += 1024u;
+                    double none[1][expansions(0)];
+                    mul_add4<0, false, true>(col, stride, none, status, xa, xb);
+                }
+                since_norm += 8 * U;
+                if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
+                    bound_column(col, stride);
+                    since_norm = 0;
+                }
+            }
+            w.st = status;
+        }
+        // rows the full rounds do not cover (fewer than 128 * (U + 1)): they lie in ONE chunk, the last
+        {
+            const long long r0 = rounds * U * 128;
+            const int synced = rounds > 0 ? (int)((rounds - 1) / RPC) + 1 : 0;       // chunks whose barrier has been passed
+            if (r0 < nrows) {
+                const int chunk = (int)(r0 / kGemvTChunk);
+                if (chunk >= synced) {
+                    cp_async_wait_all();
+                    __syncthreads();
+                }
+                unsigned status = w.st;
+                double none[1][expansions(0)];
+                const unsigned xb = xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u);
+                for (long long rr = r0 + lane; rr < nrows; rr += 32) {               // <= 36 rows per lane
+                    const double xv = lds_f64(xb + 8u * (unsigned)(rr - (long long)chunk * kGemvTChunk));
+                    mul_add1<0, false>(col, stride, none, status, prm.a[j * prm.rs + rr], xv);
+                }
+                w.st = status;
+            }
+        }
+        // ---- end of the column: drain, warp-sum the 32 private columns, round, store ----
+        w = win_flush_products(w, col, stride);
+        bound_column(col, stride);
+        const unsigned st_all = __reduce_or_sync(0xffffffffu, w.st);
+        w.st = 0u;
+        for (int jl = 0; jl < kLimbs; ++jl) {
+            const unsigned addr = col + jl * stride;
+            long long v = (long long)lds64(addr);
+            if (__any_sync(0xffffffffu, v != 0)) {
+                sts64(addr, 0ull);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // 32 x (2^52 + 2^11) < 2^58
+            }
+            if (lane == 0) wl[jl] = v;
+        }
+        __syncwarp();
+        if (lane == 0 && valid) gemv_t_store(wl, st_all, prm.y + jraw * prm.incy, prm.beta, prm.round_mode, &prm.ws->status);
+        __syncwarp();
     }
 }
 

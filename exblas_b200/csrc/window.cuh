@@ -1,0 +1,189 @@
+// window.cuh -- register-resident window of the superaccumulator (superaccumulator-only mode, F == 0).
+//
+// The reference's "superacc only" kernels (ExSUM.Superacc.cl:212-294, ExDOT.Superacc.cl:218-320,
+// ExGEMV.Superacc.cl:192-290) send every summand to the 39-limb accumulator in local memory.  On
+// B200 the shared-memory read-modify-write of a deposit costs ~25 issue slots, which makes ExDOT and
+// ExGEMV (two deposits per element) issue-bound well below the HBM rate.  Most real vectors are
+// narrow: all their products sit within a few dozen binades of each other.  For those a thread keeps
+// a WINDOW of three consecutive 52-bit digits of the accumulator in registers, anchored at a
+// per-thread exponent `b`:
+//
+//      digit k (k = 0, 1, 2) counts units of u_k = 2^(b - 52 k)
+//
+// A product p (+ its TwoProd error e, |e| <= ulp(p)/2) whose exponent lies in [b+1, b+50] is split
+// with magic-constant adds, all in the FP64 pipe:
+//      t1 = p  + M0,  x1 = t1 - M0,  r1 = p - x1        M_k = 1.5 * 2^52 * u_k
+//      t2 = r1 + M1                                      (r1 is a multiple of ulp(p) >= 2 u_1: no remainder)
+//      t3 = e  + M1,  x3 = t3 - M1,  r3 = e - x3
+//      t4 = r3 + M2                                      (e is a multiple of 2^(exp(p)-105) >= u_2: no remainder)
+// and because t_i and M_k share a binade, bits(t_i) - bits(M_k) IS the signed digit.  The thread
+// adds the raw bit patterns into three 64-bit registers and subtracts count * bits(M_k) when the
+// window is flushed (every <= 1024 elements, so no digit sum can leave 63 bits): 10 FP64 + 8 integer
+// instructions per product instead of two shared-memory deposits.  Summands outside the window take
+// the ordinary deposit; the window is flushed into the same thread-private column as four ordinary
+// deposits, so the result stays the exact sum whatever mix of paths was taken.
+//
+// Everything here is plain IEEE double arithmetic and integer bit casts, host + device, so the host
+// unit test (tests/test_window_host.py via oracle/window_check.cpp) exercises the very same code.
+#pragma once
+#include "superacc.cuh"
+
+namespace exb {
+
+#if defined(__CUDA_ARCH__)
+#define EXB_ADD(a, b) __dadd_rn((a), (b))
+#define EXB_SUB(a, b) __dsub_rn((a), (b))
+EXB_HD unsigned long long win_bits(double x) { return (unsigned long long)__double_as_longlong(x); }
+EXB_HD double win_from_bits(unsigned long long u) { return __longlong_as_double((long long)u); }
+#else
+#define EXB_ADD(a, b) ((a) + (b))
+#define EXB_SUB(a, b) ((a) - (b))
+EXB_HD unsigned long long win_bits(double x) { unsigned long long u; std::memcpy(&u, &x, 8); return u; }
+EXB_HD double win_from_bits(unsigned long long u) { double x; std::memcpy(&x, &u, 8); return x; }
+#endif
+
+constexpr int kWinFlushEvery = 1024;        // products per window between flushes
+constexpr int kWinBMin = -880;              // u_2 = 2^(b-104) and every TwoProd error stay normal
+constexpr int kWinBMax = 900;               // 2^11 * 2^52 * u_0 stays below 2^988
+constexpr unsigned kWinSpanProd = 50u << 20;   // exponent of p in [b+1, b+50]
+constexpr unsigned kWinSpanSum = 51u << 20;    // exponent of x in [b, b+50]   (single summands: two digits)
+
+struct Window {
+    unsigned long long a0, a1, a2;   // sums of raw bit patterns, one per digit
+    double M0, M1, M2;               // magic constants of the three digits
+    unsigned key0;                   // high word of 2^(b+1): in-window  <=>  (|hi| - key0) < span
+    unsigned span;                   // kWinSpanProd when anchored, 0 when the window is not in use
+    unsigned cnt;                    // products accumulated since the last flush
+    unsigned misses;                 // consecutive groups in which this thread had a summand outside
+    unsigned st;                     // status flags raised by the ordinary deposits of this thread
+};
+
+EXB_HD void win_reset(Window& w) {
+    w.a0 = w.a1 = w.a2 = 0ull;
+    w.M0 = w.M1 = w.M2 = 0.0;
+    w.key0 = 0u;
+    w.span = 0u;
+    w.cnt = 0u;
+    w.misses = 0u;
+    w.st = 0u;
+}
+
+// Anchor an EMPTY window so that a value with high word `hi` sits in the middle of it.
+// Returns false (window left unused) for zeros, specials and values too close to the layout edges.
+EXB_HD bool win_anchor(Window& w, unsigned hi) {
+    const int E = (int)((hi >> 20) & 0x7ffu);
+    if (E == 0 || E == 0x7ff) return false;
+    int b = E - 1023 - 25;
+    if (b < kWinBMin || b > kWinBMax) return false;
+    const unsigned long long m0 = ((unsigned long long)(unsigned)(b + 52 + 1023) << 52) | 0x0008000000000000ull;   // 1.5 * 2^(b+52)
+    w.M0 = win_from_bits(m0);
+    w.M1 = win_from_bits(m0 - (52ull << 52));
+    w.M2 = win_from_bits(m0 - (104ull << 52));
+    w.a0 = w.a1 = w.a2 = 0ull;
+    w.key0 = (unsigned)(b + 1 + 1023) << 20;
+    w.span = kWinSpanProd;
+    w.cnt = 0u;
+    return true;
+}
+
+// exponent of the double with high word `hi` in [b+1, b+50]
+EXB_HD bool win_holds(const Window& w, unsigned hi) { return ((hi & 0x7fffffffu) - w.key0) < w.span; }
+
+// p + e (TwoProductFMA of two doubles, p in the window) into the three digits
+EXB_HD void win_add_product(Window& w, double p, double e) {
+    const double t1 = EXB_ADD(p, w.M0);
+    const double x1 = EXB_SUB(t1, w.M0);
+    const double r1 = EXB_SUB(p, x1);
+    const double t2 = EXB_ADD(r1, w.M1);
+    const double t3 = EXB_ADD(e, w.M1);
+    const double x3 = EXB_SUB(t3, w.M1);
+    const double r3 = EXB_SUB(e, x3);
+    const double t4 = EXB_ADD(r3, w.M2);
+    w.a0 += win_bits(t1);
+    w.a1 += win_bits(t2) + win_bits(t3);
+    w.a2 += win_bits(t4);
+}
+
+// The window's content as four doubles whose exact sum it is (each an integer below 2^52, or the
+// signed top carry, times a power of two), and the window emptied.  out[] entries may be zero.
+EXB_HD void win_drain(Window& w, double (&out)[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    if (w.cnt == 0u) return;
+    const unsigned long long c = w.cnt;
+    long long d0 = (long long)(w.a0 - c * win_bits(w.M0));
+    long long d1 = (long long)(w.a1 - 2ull * c * win_bits(w.M1));
+    long long d2 = (long long)(w.a2 - c * win_bits(w.M2));
+    d1 += d2 >> kDigits;
+    d2 &= kLimbMask;
+    d0 += d1 >> kDigits;
+    d1 &= kLimbMask;
+    const long long top = d0 >> kDigits;                       // |top| <= 2^10
+    d0 &= kLimbMask;
+    // units: u_k = M_k / (1.5 * 2^52), built by exponent-field edits of the magic constants
+    const unsigned long long e0 = (win_bits(w.M0) >> 52) - 52ull;       // biased exponent of u_0
+    const double u0 = win_from_bits(e0 << 52), u1 = win_from_bits((e0 - 52ull) << 52), u2 = win_from_bits((e0 - 104ull) << 52);
+    const double utop = win_from_bits((e0 + 52ull) << 52);
+    out[0] = (double)d2 * u2;                                   // exact: integer < 2^52 times a power of two, all normal
+    out[1] = (double)d1 * u1;
+    out[2] = (double)d0 * u0;
+    out[3] = (double)top * utop;
+    w.a0 = w.a1 = w.a2 = 0ull;
+    w.cnt = 0u;
+}
+
+struct Window;
+EXB_HD void win_drain_single(Window& w, double (&out)[4]);
+
+// Bookkeeping of one thread after a group of summands that took the ordinary path (the warp vote
+// failed).  `mine`: this thread's own summands were all inside its window.  A thread whose summands
+// fall outside in two groups in a row drains its window through `emit` (ordinary deposits) and
+// anchors it at the first usable summand of the group (high words in hi[]).
+template <int G, class Emit>
+EXB_HD void win_after_slow_group(Window& w, bool mine, const unsigned (&hi)[G], bool single, Emit&& emit) {
+    if (mine) {
+        w.misses = 0u;
+        return;
+    }
+    if (++w.misses < 2u) return;
+    double out[4];
+    if (single) win_drain_single(w, out); else win_drain(w, out);
+    for (int k = 0; k < 4; ++k)
+        if (out[k] != 0.0) emit(out[k]);
+    w.span = 0u;
+    for (int k = 0; k < G; ++k)
+        if (win_anchor(w, hi[k])) break;
+    w.misses = 0u;
+}
+
+// Single summands (ExSUM): x with exponent in [b, b+50] needs two digits only.
+//      t1 = x + M0, x1 = t1 - M0, r1 = x - x1, t2 = r1 + M1      (r1 multiple of ulp(x) >= u_1)
+// Uses digits 0 and 1 of the same window; a1 receives ONE pattern per summand here, so a window is
+// used either for products or for single summands, never both (cnt1 = cnt).
+EXB_HD bool win_holds_sum(const Window& w, unsigned hi) { return ((hi & 0x7fffffffu) - (w.key0 - (1u << 20))) < (w.span ? kWinSpanSum : 0u); }
+EXB_HD void win_add_single(Window& w, double x) {
+    const double t1 = EXB_ADD(x, w.M0);
+    const double x1 = EXB_SUB(t1, w.M0);
+    const double r1 = EXB_SUB(x, x1);
+    const double t2 = EXB_ADD(r1, w.M1);
+    w.a0 += win_bits(t1);
+    w.a1 += win_bits(t2);
+}
+EXB_HD void win_drain_single(Window& w, double (&out)[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    if (w.cnt == 0u) return;
+    const unsigned long long c = w.cnt;
+    long long d0 = (long long)(w.a0 - c * win_bits(w.M0));
+    long long d1 = (long long)(w.a1 - c * win_bits(w.M1));
+    d0 += d1 >> kDigits;
+    d1 &= kLimbMask;
+    const long long top = d0 >> kDigits;
+    d0 &= kLimbMask;
+    const unsigned long long e0 = (win_bits(w.M0) >> 52) - 52ull;
+    out[1] = (double)d1 * win_from_bits((e0 - 52ull) << 52);
+    out[2] = (double)d0 * win_from_bits(e0 << 52);
+    out[3] = (double)top * win_from_bits((e0 + 52ull) << 52);
+    w.a0 = w.a1 = w.a2 = 0ull;
+    w.cnt = 0u;
+}
+
+}  // namespace exb

@@ -120,6 +120,24 @@ int exblas_b200_exgemv(exblas_b200_handle_t handle, char trans, int64_t m, int64
                        const double* a, int64_t lda, int64_t offseta, const double* x, int64_t incx,
                        int64_t offsetx, double beta, double* y, int64_t incy, int64_t offsety,
                        int fpe, int early_exit, int round_mode);
+/* ---- batched ("segmented") ExSUM / ExDOT ---------------------------- */
+
+/* nseg independent exact reductions in ONE launch, one warp per segment:
+ *     results[s] = round( sum_{i = seg[s]}^{seg[s+1]-1} a[i] )                    (exsum_segments)
+ *     results[s] = round( sum_{i = seg[s]}^{seg[s+1]-1} a[i] * b[ gather ? gather[i] : i ] )   (exdot_segments)
+ * seg holds nseg + 1 non-decreasing offsets.  This is what the reference's application callers do with
+ * one exsum() per short host vector (src/cpu/examples/kmeans/kmeans_clustering.cpp:213,
+ * spmv/main.cpp:85, mri-gridding/CPU_kernels.cpp:293); with a gather index it is a CSR sparse
+ * matrix-vector product (a = values, gather = column indices, seg = row pointers, b = x).
+ * statuses (optional) receives each segment's EXBLAS_B200_ST_* flags.  All pointers host, or all
+ * device (then asynchronous on the handle's stream; nb is only needed for host operands with gather:
+ * the length of b).  fpe / early_exit are accepted for symmetry and never change a result. */
+int exblas_b200_exsum_segments(exblas_b200_handle_t handle, const double* a, const int64_t* seg, int64_t nseg,
+                               int fpe, int early_exit, int round_mode, double* results, uint32_t* statuses);
+int exblas_b200_exdot_segments(exblas_b200_handle_t handle, const double* a, const double* b, const int32_t* gather,
+                               int64_t nb, const int64_t* seg, int64_t nseg, int fpe, int early_exit, int round_mode,
+                               double* results, uint32_t* statuses);
+
 /* Wait for the handle's stream and latch the status flags of the last asynchronous call. */
 int exblas_b200_sync(exblas_b200_handle_t handle);
 

@@ -135,3 +135,129 @@ def test_exgemv_large_rows_match_exdot(gpu):
     xb.exgemv("N", m, n, 1.0, A, m, 0, x, 1, 0, 0.0, y, 1, 0, 4, False, round_mode=xb.ROUND_EXACT, handle=gpu)
     want = float(Fraction(1.1) * Fraction(1.1) * n)
     assert bool((y == want).all())
+
+
+# ---- register-window kernels (exblas_b200/csrc/window.cuh): 'N' with fpe < 2, and 'T' ----
+
+def make_kind(m, n, lda, kind, seed):
+    """column-major m x n matrix (leading dimension lda), x of length max(m, n), y likewise"""
+    rng = np.random.default_rng(seed)
+    A = cm.init_fpuniform(m * n, 10, 5, seed=seed, neg_ratio=2).reshape(n, m)          # narrow: 10 binades
+    x = cm.init_fpuniform(max(m, n), 10, 5, seed=seed + 1, neg_ratio=2)
+    if kind == "rowscale":         # every row at its own magnitude: per-thread windows ('N'), drifting windows ('T')
+        A = A * np.exp2(rng.integers(-150, 150, size=m)).reshape(1, m)
+    elif kind == "colscale":
+        A = A * np.exp2(rng.integers(-150, 150, size=n)).reshape(n, 1)
+    elif kind == "drift":          # the scale moves slowly along both directions: windows must follow
+        A = A * np.exp2((np.arange(n) // 37).reshape(n, 1) * 3.0 - (np.arange(m) // 50).reshape(1, m) * 2.0)
+    elif kind == "sparse":         # exact zeros, -0.0 and a few far outliers
+        A = A.copy()
+        A[rng.random((n, m)) < 0.3] = 0.0
+        A[rng.random((n, m)) < 0.01] *= 2.0 ** 200
+        x = x.copy()
+        x[::7] = -0.0
+    elif kind == "wide":
+        A = cm.init_fpuniform(m * n, 600, 300, seed=seed, neg_ratio=2).reshape(n, m)
+    a = np.zeros(lda * n)
+    a.reshape(n, lda)[:, :m] = A
+    y = cm.init_fpuniform(max(m, n), 100, 50, seed=seed + 2, neg_ratio=2)
+    return a, x, y
+
+
+KINDS = ("narrow", "rowscale", "colscale", "drift", "sparse", "wide")
+
+
+@pytest.mark.gpu
+def test_exgemv_n_window_kernel(gpu, oracle):
+    import torch
+    import exblas_b200 as xb
+    try:
+        for (m, n, lda) in [(700, 3000, 704), (384, 70, 384), (1000, 1037, 1003), (33, 9000, 40)]:
+            for kind in KINDS:
+                a, x, y = make_kind(m, n, lda, kind, seed=m + n)
+                da, dx = torch.from_numpy(a).cuda(), torch.from_numpy(x[:n].copy()).cuda()
+                for beta in (0.0, 1.0):
+                    w0 = oracle.exgemv("N", m, n, 1.0, a, lda, x[:n], 1, beta, y[:m], 1, 0, False, 0)
+                    w1 = oracle.exgemv("N", m, n, 1.0, a, lda, x[:n], 1, beta, y[:m], 1, 0, False, 1)
+                    for window in (1, 0):
+                        gpu.set_option("window", window)
+                        for fpe in (0, 1):
+                            for rm, want in ((0, w0), (1, w1)):
+                                dy = torch.from_numpy(y[:m].copy()).cuda()
+                                xb.exgemv("N", m, n, 1.0, da, lda, 0, dx, 1, 0, beta, dy, 1, 0, fpe, False, round_mode=rm, handle=gpu)
+                                got = dy.cpu().numpy()
+                                assert (got.view(np.uint64) == want.view(np.uint64)).all(), (m, n, kind, beta, window, fpe, rm)
+                assert gpu.last_status() == 0
+        # column splits of the window kernel (x slices staged per part) and a strided x
+        m, n, lda = 500, 2500, 512
+        a, x, y = make_kind(m, n, lda, "drift", seed=5)
+        xbuf = np.full(3 * n, 9.0)
+        xbuf[1::3][:n] = x[:n]
+        want = oracle.exgemv("N", m, n, 1.0, a, lda, x[:n], 1, 1.0, y[:m], 1, 0, False, 0)
+        gpu.set_option("window", 1)
+        for parts in (1, 2, 7, 40):
+            gpu.set_option("gemv_parts", parts)
+            dy = torch.from_numpy(y[:m].copy()).cuda()
+            xb.exgemv("N", m, n, 1.0, torch.from_numpy(a).cuda(), lda, 0, torch.from_numpy(xbuf).cuda(), 3, 1, 1.0, dy, 1, 0, 0, False, handle=gpu)
+            assert (dy.cpu().numpy().view(np.uint64) == want.view(np.uint64)).all(), parts
+    finally:
+        gpu.set_option("window", 1)
+        gpu.set_option("gemv_parts", 0)
+
+
+@pytest.mark.gpu
+def test_exgemv_t_kernels(gpu, oracle):
+    """'T': y_j = sum_i A[i, j] x[i].  Columns >= 256 rows run the warp-per-output window kernel (both
+    launch shapes), shorter ones the strided thread-per-output kernel; all must equal the oracle."""
+    import torch
+    import exblas_b200 as xb
+    try:
+        for (m, n, lda) in [(300, 40, 300), (2048, 24, 2048), (5000, 17, 5003), (255, 10, 256), (4224, 30, 4224), (3200, 9, 3201),
+                            (1151, 13, 1152)]:
+            for kind in KINDS:
+                a, x, y = make_kind(m, n, lda, kind, seed=2 * m + n)
+                da, dx = torch.from_numpy(a).cuda(), torch.from_numpy(x[:m].copy()).cuda()
+                for alpha, beta in ((1.0, 0.0), (1.0, 1.0), (1.0, -2.5), (0.3, 1.0)):
+                    w0 = oracle.exgemv("T", m, n, alpha, a, lda, x[:m], 1, beta, y[:n], 1, 0, False, 0)
+                    w1 = oracle.exgemv("T", m, n, alpha, a, lda, x[:m], 1, beta, y[:n], 1, 0, False, 1)
+                    for shape in (0, 1):
+                        gpu.set_option("gemv_t_shape", shape)
+                        for fpe, ee in ((0, False), (3, False), (8, True)):
+                            for rm, want in ((0, w0), (1, w1)):
+                                dy = torch.from_numpy(y[:n].copy()).cuda()
+                                xb.exgemv("T", m, n, alpha, da, lda, 0, dx, 1, 0, beta, dy, 1, 0, fpe, ee, round_mode=rm, handle=gpu)
+                                got = dy.cpu().numpy()
+                                assert (got.view(np.uint64) == want.view(np.uint64)).all(), (m, n, kind, alpha, beta, shape, fpe, ee, rm)
+                assert gpu.last_status() == 0
+        # offsets and strides through the window kernel
+        m, n, lda = 2100, 19, 2104
+        a, x, y = make_kind(m, n, lda, "rowscale", seed=9)
+        offa, offx, offy, incx, incy = 3, 2, 1, 2, 3
+        abuf = np.concatenate([np.full(offa, 9.0), a])
+        xbuf = np.full(offx + (m - 1) * incx + 1, 7.0)
+        xbuf[offx::incx][:m] = x[:m]
+        ybuf = np.full(offy + (n - 1) * incy + 1, 5.0)
+        ybuf[offy::incy][:n] = y[:n]
+        want = oracle.exgemv("T", m, n, 1.0, a, lda, x[:m], 1, 1.0, y[:n], 1, 0, False, 0)
+        for shape in (0, 1):
+            gpu.set_option("gemv_t_shape", shape)
+            dy = torch.from_numpy(ybuf.copy()).cuda()
+            xb.exgemv("T", m, n, 1.0, torch.from_numpy(abuf).cuda(), lda, offa, torch.from_numpy(xbuf).cuda(), incx, offx, 1.0, dy,
+                      incy, offy, 0, False, handle=gpu)
+            out = dy.cpu().numpy()
+            assert (out[offy::incy][:n].view(np.uint64) == want.view(np.uint64)).all(), shape
+            mask = np.ones(out.size, dtype=bool)
+            mask[offy::incy] = False
+            assert (out[mask] == 5.0).all()
+        # specials keep their IEEE meaning through the window kernels
+        m, n = 1024, 8
+        a, x, y = make_kind(m, n, m, "narrow", seed=4)
+        a2 = a.copy()
+        a2[5] = np.inf
+        a2[m + 7] = np.nan
+        dy = torch.zeros(n, dtype=torch.float64, device="cuda")
+        xb.exgemv("T", m, n, 1.0, torch.from_numpy(a2).cuda(), m, 0, torch.from_numpy(x[:m].copy()).cuda(), 1, 0, 0.0, dy, 1, 0, 0, False, handle=gpu)
+        out = dy.cpu().numpy()
+        assert np.isinf(out[0]) and np.isnan(out[1]) and np.isfinite(out[2:]).all()
+    finally:
+        gpu.set_option("gemv_t_shape", 0)
