@@ -415,6 +415,36 @@ def run_ours(args, fpes):
                   "workload": f"ExDOT n=2^{args.log2n} per GPU, cancelling ill-conditioned pairs (cond > 1e32), "
                               f"exact result {1.5 * world}; aggregate GB/s over {world} GPU(s), 16 B/element"}
         del xa, xb_
+        torch.cuda.empty_cache()
+        # BASELINE config 5: ExGEMV 32768 x 32768, the reference test's fp-uniform data ("10 0": 10 binades),
+        # 'N' and 'T', superaccumulator-only (register window) and FPE 3; GB/s = (m*n + m + n) * 8 / t as the
+        # reference reports it (ExGEMV.cpp:208-211).  One GPU only (the matrix is not sharded).
+        if world == 1 and args.log2n >= 30:
+            gm = 32768
+            A = torch.empty(gm * gm, dtype=torch.float64, device=dev)
+            for lo in range(0, gm * gm, 1 << 27):
+                A[lo:lo + (1 << 27)] = cm.init_fpuniform(gm * gm, 10, 5, seed=1, neg_ratio=2, lo=lo, hi=lo + (1 << 27), device=dev)
+            gx = cm.init_fpuniform(gm, 10, 5, seed=2, neg_ratio=2, device=dev)
+            gy = torch.zeros(gm, dtype=torch.float64, device=dev)
+            gv = {}
+            ys = {}
+            for trans in ("N", "T"):
+                for f in (0, 3):
+                    for _ in range(2):
+                        xb.exgemv(trans, gm, gm, 1.0, A, gm, 0, gx, 1, 0, 0.0, gy, 1, 0, f, False, handle=h, sync=False)
+                    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    d0.record(stream)
+                    for _ in range(5):
+                        xb.exgemv(trans, gm, gm, 1.0, A, gm, 0, gx, 1, 0, 0.0, gy, 1, 0, f, False, handle=h, sync=False)
+                    d1.record(stream)
+                    d1.synchronize()
+                    ms = d0.elapsed_time(d1) / 5
+                    gv[f"{trans} fpe{f}"] = {"ms": round(ms, 3), "GBs": round((gm * gm + 2 * gm) * 8 / (ms * 1e-3) / 1e9, 1)}
+                    ys[(trans, f)] = gy.clone()
+            gv["fpe_variants_bit_identical"] = bool((ys[("N", 0)].view(torch.int64) == ys[("N", 3)].view(torch.int64)).all()
+                                                    and (ys[("T", 0)].view(torch.int64) == ys[("T", 3)].view(torch.int64)).all())
+            extras["exgemv_32768"] = gv
+            del A, gx, gy, ys
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -108,7 +108,8 @@ struct exblas_b200_handle_s {
     int64_t opt_host_chunk = (int64_t)1 << 23;
     int64_t opt_adaptive = 1;
     int64_t opt_gemv_parts = 0;
-    int64_t opt_gemv_t_shape = 0;
+    int64_t opt_gemv_t_shape = 2;
+    int64_t opt_gemv_n_shape = 1;
     int64_t opt_window = 1;                 // register window in the superaccumulator-only kernels (performance only)
     void* comm = nullptr;
     int nranks = 1;
@@ -451,27 +452,42 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
         p.beta = beta;
         p.ws = h->d_ws;
         p.round_mode = round_mode;
-        // two shapes (option "gemv_t_shape"): 0 = 256 threads x 8 groups in flight (no register spills),
-        // 1 = 384 threads x 6 groups
-        const bool wide = h->opt_gemv_t_shape == 1;
-        const int T = wide ? 384 : 256, nwarps = T / 32, chunk = wide ? 6144 : 8192;
+        // launch shapes (option "gemv_t_shape"): threads x groups of 4 rows in flight per lane x rows of x per buffer
+        struct TShape { int T, chunk; gemv_fn fn; };
+        static const TShape shapes[] = {
+            {256, 8192, exgemv_t_win_kernel<8, 256, 8192>},
+            {384, 6144, exgemv_t_win_kernel<6, 384, 6144>},
+            {512, 4096, exgemv_t_win_kernel<4, 512, 4096>},
+            {512, 3072, exgemv_t_win_kernel<3, 512, 3072>},
+        };
+        const TShape& sh = shapes[h->opt_gemv_t_shape];
+        const int T = sh.T, nwarps = T / 32, chunk = sh.chunk;
         const int64_t nsets = (m + nwarps - 1) / nwarps;
         const unsigned grid = (unsigned)(nsets < h->num_sms ? nsets : h->num_sms);
         const size_t smem = ((size_t)T * kLimbs + 2 * (size_t)chunk + 40 * (size_t)nwarps) * sizeof(long long);
-        gemv_fn fn = wide ? exgemv_t_win_kernel<6, 384, 6144> : exgemv_t_win_kernel<8, 256, 8192>;
+        gemv_fn fn = sh.fn;
         CK(allow_big_smem((const void*)fn, h->device));
         void* args[] = {(void*)&p};
         CK(cudaLaunchKernel((const void*)fn, dim3(grid), dim3((unsigned)T), args, smem, h->stream));
         h->launches += 1;
         return EXBLAS_B200_OK;
     }
-    int T = kGemvT;
-    if (m < T) T = (int)((m + 31) / 32 * 32);
-    if (T < 32) T = 32;
-    const int64_t row_blocks = (m + T - 1) / T;
     // superaccumulator-only mode, alpha == 1, unit row stride: the register-window kernel (window.cuh);
     // it stages its slice of x in shared memory, so a part holds at most kGemvXsMax columns
     const bool windowed = f == 0 && alpha == 1.0 && rs == 1 && h->opt_window;
+    // launch shapes of the window kernel (option "gemv_n_shape"): rows per CTA x column groups in flight
+    struct NShape { int T; gemv_fn fn; };
+    static const NShape nshapes[] = {
+        {384, exgemv_n_win_kernel<8, 384>},
+        {512, exgemv_n_win_kernel<4, 512>},
+        {512, exgemv_n_win_kernel<5, 512>},
+    };
+    const NShape& nsh = nshapes[h->opt_gemv_n_shape];
+    const int Tmax = windowed ? nsh.T : kGemvT;
+    int T = Tmax;
+    if (m < T) T = (int)((m + 31) / 32 * 32);
+    if (T < 32) T = 32;
+    const int64_t row_blocks = (m + T - 1) / T;
     const int pmin = windowed ? (int)((n + kGemvXsMax - 1) / kGemvXsMax) : 1;
     int parts = h->opt_gemv_parts > 0 ? (int)h->opt_gemv_parts : choose_gemv_parts(row_blocks, n, h->num_sms, pmin > 0 ? pmin : 1);
     if (parts < pmin) parts = pmin;
@@ -508,9 +524,8 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     p.round_mode = round_mode;
     p.adaptive = h->opt_adaptive ? 1 : 0;
     p.x_vec_ok = (incx == 1 && ((uintptr_t)x % 32) == 0) ? 1 : 0;       // part starts are multiples of 4 columns
-    gemv_fn fn = windowed ? exgemv_n_win_kernel<kGemvWinU, kGemvT>
-                          : (alpha == 1.0 ? select_gemv<true>(f, ee) : select_gemv<false>(f, ee));
-    const size_t smem = windowed ? (size_t)kGemvT * kLimbs * sizeof(long long) + (size_t)cpp * sizeof(double)   // fixed limb stride
+    gemv_fn fn = windowed ? nsh.fn : (alpha == 1.0 ? select_gemv<true>(f, ee) : select_gemv<false>(f, ee));
+    const size_t smem = windowed ? (size_t)Tmax * kLimbs * sizeof(long long) + (size_t)cpp * sizeof(double)   // fixed limb stride
                                  : (size_t)T * kLimbs * sizeof(long long);
     CK(allow_big_smem((const void*)fn, h->device));
     void* args[] = {(void*)&p};
@@ -736,8 +751,11 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
         if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;
         h->opt_gemv_parts = value;
     } else if (!strcmp(name, "gemv_t_shape")) {
-        if (value < 0 || value > 1) return EXBLAS_B200_EINVAL;
+        if (value < 0 || value > 3) return EXBLAS_B200_EINVAL;
         h->opt_gemv_t_shape = value;
+    } else if (!strcmp(name, "gemv_n_shape")) {
+        if (value < 0 || value > 2) return EXBLAS_B200_EINVAL;
+        h->opt_gemv_n_shape = value;
     } else if (!strcmp(name, "window")) {
         h->opt_window = value != 0;
     } else if (!strcmp(name, "adaptive")) {

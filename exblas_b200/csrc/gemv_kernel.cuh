@@ -48,12 +48,6 @@ EXB_D Vec4 ldg256_cached(const double* p) {     // through L1: x is re-read by e
     return r;
 }
 
-EXB_D double ldg64(const double* p) {
-    double r;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
-    return r;
-}
-
 template <int F, bool EE, bool ALPHA1, int U, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm) {
     extern __shared__ long long smem[];
@@ -301,6 +295,8 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
     const double* qa = prm.a + row * prm.rs + cs * c0;       // next group of A to load
     const long long astep = 4 * cs;
     double va[U][4];
+    // (Refills are predicated on "there is a next round".  Making them unconditional by parking the pointer in
+    // the last round was measured 30 % slower: the compiler hoists the loads and spills the window.)
     auto load_group = [&](int u) {
         va[u][0] = ldg64(qa);
         va[u][1] = ldg64(qa + cs);
@@ -457,6 +453,9 @@ constexpr int kGemvTChunk = EXB_TCHUNK;   // rows of x staged per buffer
 
 template <int U, int MAXT, int kGemvTChunk>
 __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams prm) {
+    // (A variant in which lane l reads rows 4l .. 4l+3 with one 256-bit load was measured slower: its
+    // x reads, 32 bytes apart per lane, conflict in shared memory, and the wider requests bought nothing.)
+    constexpr bool VEC = false;
     // here prm.m = number of outputs (columns of A), prm.n = rows summed per output, prm.rs = lda, prm.cs = 1
     extern __shared__ long long smem[];
     const unsigned T = blockDim.x;                                                   // <= MAXT
@@ -491,15 +490,27 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
         const long long jraw = set * nwarps + warp;
         const bool valid = jraw < nout;
         const long long j = valid ? jraw : nout - 1;                                 // spare warps redo the last column (they must meet the barriers)
-        const double* colp = prm.a + j * prm.rs + lane;                              // row `lane` of column j
-        const double* qa = colp;
+        const double* qa = prm.a + j * prm.rs + (VEC ? 4u * lane : lane);            // this lane's first row of column j
         double va[U][4];
         auto load_group = [&](int u) {
-            va[u][0] = ldg64(qa);
-            va[u][1] = ldg64(qa + 32);
-            va[u][2] = ldg64(qa + 64);
-            va[u][3] = ldg64(qa + 96);
+            if (VEC) {
+                const Vec4 v = ldg256(qa);
+                va[u][0] = v.x; va[u][1] = v.y; va[u][2] = v.z; va[u][3] = v.w;
+            } else {
+                va[u][0] = ldg64(qa);
+                va[u][1] = ldg64(qa + 32);
+                va[u][2] = ldg64(qa + 64);
+                va[u][3] = ldg64(qa + 96);
+            }
             qa += 128;
+        };
+        auto load_x = [&](unsigned xaddr, double& x0, double& x1, double& x2, double& x3) {
+            if (VEC) {
+                lds128(xaddr, x0, x1);
+                lds128(xaddr + 16u, x2, x3);
+            } else {
+                x0 = lds_f64(xaddr); x1 = lds_f64(xaddr + 256u); x2 = lds_f64(xaddr + 512u); x3 = lds_f64(xaddr + 768u);
+            }
         };
         const long long rounds = full_groups / U;
 #pragma unroll
@@ -517,7 +528,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
                 __syncthreads();                                                     // chunk resident; buffer (chunk + 1) & 1 is free
                 if (chunk + 1 < nchunks) stage(chunk + 1);
             }
-            return xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u) + (unsigned)(r % RPC) * (128u * U * 8u) + 8u * lane;
+            return xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u) + (unsigned)(r % RPC) * (128u * U * 8u) + (VEC ? 32u : 8u) * lane;
         };
         long long r = 0;
         // ---- loop 1: register window; two rounds in a row that mostly miss end it (for this and the next 7 columns) ----
@@ -530,7 +541,8 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
             for (int u = 0; u < U; ++u) {
                 const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
                 if (has_next) load_group(u);
-                const double x0 = lds_f64(xaddr), x1 = lds_f64(xaddr + 256u), x2 = lds_f64(xaddr + 512u), x3 = lds_f64(xaddr + 768u);
+                double x0, x1, x2, x3;
+                load_x(xaddr, x0, x1, x2, x3);
                 xaddr += 1024u;
                 const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
                 const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
@@ -571,7 +583,8 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
                 for (int u = 0; u < U; ++u) {
                     const double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
                     if (has_next) load_group(u);
-                    const double xb[4] = {lds_f64(xaddr), lds_f64(xaddr + 256u), lds_f64(xaddr + 512u), lds_f64(xaddr + 768u)};
+                    double xb[4];
+                    load_x(xaddr, xb[0], xb[1], xb[2], xb[3]);
                     xaddr += 1024u;
                     double none[1][expansions(0)];
                     mul_add4<0, false, true>(col, stride, none, status, xa, xb);

@@ -89,6 +89,12 @@ EXB_D Vec4 ldg256(const double* p) {
     return r;
 }
 
+EXB_D double ldg64(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
 EXB_D void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -502,7 +508,40 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
         const long long nscalar = prm.n - body;            // head + tail (or everything)
         const long long gthreads = (long long)gridDim.x * T;
         int since_norm = 0;
-        for (long long k = (long long)blockIdx.x * T + tid; k < nscalar; k += gthreads) {
+        long long k = (long long)blockIdx.x * T + tid;
+        // Strided vectors (inca / incb != 1: no vector body at all) and long tails: eight independent
+        // loads per thread in flight, consumed four at a time through the same four-summand code as
+        // the vector body (per-thread early exit: lanes need not be converged here).  A warp load of
+        // 32 consecutive elements touches 32 * inc * 8 bytes, so the useful fraction of every sector
+        // is 1 / inc whatever is done here; what this loop buys is memory-level parallelism.
+        for (; k + 7 * gthreads < nscalar; k += 8 * gthreads) {
+            double xa[8], xb[DOT ? 8 : 1];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long kk = k + j * gthreads;
+                const long long idx = kk < prm.head ? kk : kk + body;
+                xa[j] = ldg64(prm.a + idx * prm.inca);
+                if (DOT) xb[j] = ldg64(prm.b + idx * prm.incb);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double x4[4] = {xa[4 * h], xa[4 * h + 1], xa[4 * h + 2], xa[4 * h + 3]};
+                if (DOT) {
+                    const double y4[4] = {xb[4 * h], xb[4 * h + 1], xb[4 * h + 2], xb[4 * h + 3]};
+                    mul_add4<F, EE, false>(col, stride, a, status, x4, y4);
+                } else if (F == 0) {
+                    deposit4<false>(col, stride, x4[0], x4[1], x4[2], x4[3], status);
+                } else {
+                    add4<F, EE, false>(col, stride, a, status, x4);
+                }
+            }
+            since_norm += 8 * kDepPerElem;
+            if (since_norm > kMaxDepositsPerNormalize - 8 * kDepPerElem - 2 * kM * (F + 2)) {
+                bound_column(col, stride);
+                since_norm = 0;
+            }
+        }
+        for (; k < nscalar; k += gthreads) {
             const long long idx = k < prm.head ? k : k + body;
             if (DOT) mul_add1<F, EE>(col, stride, a, status, prm.a[idx * prm.inca], prm.b[idx * prm.incb]);
             else add1<F, EE>(col, stride, a, status, prm.a[idx * prm.inca]);

@@ -75,6 +75,14 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{rnd}_*.ncu-
     print("wrote", name)
 
 # bench.py looks the dominant kernel's traffic up by "<op>_2p30"
+old_tj = {}
+tpath = os.path.join(out_dir, "traffic.json")
+if os.path.exists(tpath):          # captures of earlier sessions whose .ncu-rep files are gone: keep their entries
+    try:
+        old_tj = json.load(open(tpath))
+    except Exception:
+        old_tj = {}
+traffic = {**old_tj.get("all", {}), **traffic}
 tj = {}
 for k, v in traffic.items():
     if k.startswith("exsum") and "logu" in k:

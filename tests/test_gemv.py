@@ -179,14 +179,15 @@ def test_exgemv_n_window_kernel(gpu, oracle):
                 for beta in (0.0, 1.0):
                     w0 = oracle.exgemv("N", m, n, 1.0, a, lda, x[:n], 1, beta, y[:m], 1, 0, False, 0)
                     w1 = oracle.exgemv("N", m, n, 1.0, a, lda, x[:n], 1, beta, y[:m], 1, 0, False, 1)
-                    for window in (1, 0):
+                    for window, nshape in ((1, 0), (1, 1), (1, 2), (0, 0)):
                         gpu.set_option("window", window)
+                        gpu.set_option("gemv_n_shape", nshape)
                         for fpe in (0, 1):
                             for rm, want in ((0, w0), (1, w1)):
                                 dy = torch.from_numpy(y[:m].copy()).cuda()
                                 xb.exgemv("N", m, n, 1.0, da, lda, 0, dx, 1, 0, beta, dy, 1, 0, fpe, False, round_mode=rm, handle=gpu)
                                 got = dy.cpu().numpy()
-                                assert (got.view(np.uint64) == want.view(np.uint64)).all(), (m, n, kind, beta, window, fpe, rm)
+                                assert (got.view(np.uint64) == want.view(np.uint64)).all(), (m, n, kind, beta, window, nshape, fpe, rm)
                 assert gpu.last_status() == 0
         # column splits of the window kernel (x slices staged per part) and a strided x
         m, n, lda = 500, 2500, 512
@@ -203,6 +204,7 @@ def test_exgemv_n_window_kernel(gpu, oracle):
     finally:
         gpu.set_option("window", 1)
         gpu.set_option("gemv_parts", 0)
+        gpu.set_option("gemv_n_shape", 1)
 
 
 @pytest.mark.gpu
@@ -220,9 +222,9 @@ def test_exgemv_t_kernels(gpu, oracle):
                 for alpha, beta in ((1.0, 0.0), (1.0, 1.0), (1.0, -2.5), (0.3, 1.0)):
                     w0 = oracle.exgemv("T", m, n, alpha, a, lda, x[:m], 1, beta, y[:n], 1, 0, False, 0)
                     w1 = oracle.exgemv("T", m, n, alpha, a, lda, x[:m], 1, beta, y[:n], 1, 0, False, 1)
-                    for shape in (0, 1):
+                    for shape in (0, 1, 2, 3):
                         gpu.set_option("gemv_t_shape", shape)
-                        for fpe, ee in ((0, False), (3, False), (8, True)):
+                        for fpe, ee in ((0, False), (8, True)):
                             for rm, want in ((0, w0), (1, w1)):
                                 dy = torch.from_numpy(y[:n].copy()).cuda()
                                 xb.exgemv("T", m, n, alpha, da, lda, 0, dx, 1, 0, beta, dy, 1, 0, fpe, ee, round_mode=rm, handle=gpu)
@@ -239,7 +241,7 @@ def test_exgemv_t_kernels(gpu, oracle):
         ybuf = np.full(offy + (n - 1) * incy + 1, 5.0)
         ybuf[offy::incy][:n] = y[:n]
         want = oracle.exgemv("T", m, n, 1.0, a, lda, x[:m], 1, 1.0, y[:n], 1, 0, False, 0)
-        for shape in (0, 1):
+        for shape in (0, 1, 2, 3):
             gpu.set_option("gemv_t_shape", shape)
             dy = torch.from_numpy(ybuf.copy()).cuda()
             xb.exgemv("T", m, n, 1.0, torch.from_numpy(abuf).cuda(), lda, offa, torch.from_numpy(xbuf).cuda(), incx, offx, 1.0, dy,
@@ -260,4 +262,4 @@ def test_exgemv_t_kernels(gpu, oracle):
         out = dy.cpu().numpy()
         assert np.isinf(out[0]) and np.isnan(out[1]) and np.isfinite(out[2:]).all()
     finally:
-        gpu.set_option("gemv_t_shape", 0)
+        gpu.set_option("gemv_t_shape", 2)
