@@ -181,7 +181,6 @@ kernel_fn select_kernel(int f, bool ee) {
         }
     }
     switch (f) {
-        case 0: return kernel_ptr<0, false, DOT>();
         case 2: return kernel_ptr<2, false, DOT>();
         case 3: return kernel_ptr<3, false, DOT>();
         case 4: return kernel_ptr<4, false, DOT>();
@@ -208,6 +207,7 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     p.round_mode = round_mode;
     p.keep = 0;
     p.adaptive = h->opt_adaptive ? 1 : 0;
+    p.window = h->opt_window ? 1 : 0;
     p.fresh = h->acc_pending ? 0 : 1;
     p.nranks = 0;
     if (finalize && h->peer_ranks > 1 && h->opt_fused) {          // closing launch: exchange limbs inside the kernel
@@ -226,7 +226,8 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
         else if (n <= (1 << 15)) { max_blocks = 1; }
         else if (n <= (1 << 18)) { T = 128; }          // small CTAs, little shared memory to clear
     }
-    const int U = vectors_in_flight(f, ee, dot);
+    // superaccumulator-only kernels (exblas_reduce0_kernel) tile by rows of T * 4 elements
+    const int U = f == 0 ? 1 : vectors_in_flight(f, ee, dot);
     const int64_t tile = (int64_t)T * 4 * U;
 
     // vector body needs unit strides and, for ExDOT, the same 32-byte phase on both streams
@@ -250,7 +251,10 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     if (want < 1) want = 1;
     if (blocks > want) blocks = want;
 
-    kernel_fn fn = dot ? select_kernel<true>(f, ee) : select_kernel<false>(f, ee);
+    // superaccumulator-only mode: window loop with 6 (ExSUM) / 2 (ExDOT) rows in flight, direct loop with 8 / 4
+    // (measured at n = 2^30 against 4/8, 8/8 and 3/4, 4/4: profiles/f0_window_r01.jsonl)
+    kernel_fn fn = f == 0 ? (dot ? exblas_reduce0_kernel<true, 2, 4, kMaxT> : exblas_reduce0_kernel<false, 6, 8, kMaxT>)
+                          : (dot ? select_kernel<true>(f, ee) : select_kernel<false>(f, ee));
     const size_t smem = (size_t)T * kLimbs * sizeof(long long);
     CK(allow_big_smem((const void*)fn, h->device));
     void* args[] = {(void*)&p};

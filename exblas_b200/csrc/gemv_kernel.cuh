@@ -22,7 +22,6 @@
 //   * beta*y is added exactly (TwoProd) as ExGEMV.FPE.cl:346-377 does, for any beta.
 #pragma once
 #include "reduce_kernel.cuh"
-#include "window.cuh"
 
 namespace exb {
 
@@ -231,36 +230,6 @@ EXB_D void lds128(unsigned addr, double& x, double& y) {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
 }
 
-// Ordinary path for one group of four columns + window bookkeeping (rare: out of line, by value so
-// that the window stays in registers in the hot loop).
-__device__ __noinline__ Window gemv_slow_group(Window w, unsigned col, unsigned stride, double a0, double a1, double a2,
-                                               double a3, double x0, double x1, double x2, double x3, bool mine,
-                                               bool track) {
-    const double xa[4] = {a0, a1, a2, a3}, xb[4] = {x0, x1, x2, x3};
-    double none[1][expansions(0)];
-    unsigned status = w.st;
-    mul_add4<0, false, false>(col, stride, none, status, xa, xb);
-    if (track) {
-        unsigned hi[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) hi[k] = (unsigned)__double2hiint(__dmul_rn(xa[k], xb[k]));
-        win_after_slow_group<4>(w, mine, hi, false, [&](double v) { deposit(col, stride, v, status); });
-    }
-    w.st = status;
-    return w;
-}
-
-__device__ __noinline__ Window win_flush_products(Window w, unsigned col, unsigned stride) {
-    double out[4];
-    win_drain(w, out);
-    unsigned status = w.st;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (out[k] != 0.0) deposit(col, stride, out[k], status);
-    w.st = status;
-    return w;
-}
-
 constexpr int kGemvXsMax = 8192;          // doubles of x staged per CTA (64 KB)
 
 template <int U, int MAXT>
@@ -337,7 +306,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
                 win_add_product(w, p3, __fma_rn(a3, x3, -p3));
                 w.cnt += 4u;
             } else {
-                w = gemv_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
+                w = prod_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
                 ++missed;
             }
         }
@@ -383,7 +352,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
         const double* ra = prm.a + row * prm.rs + cs * (c0 + (long long)rounds * U * 4);
         for (int g = rounds * U; g < ngroups; ++g, ra += astep) {
             const double* xg = xs + 4 * g;
-            w = gemv_slow_group(w, col, stride, ra[0], ra[cs], ra[2 * cs], ra[3 * cs], xg[0], xg[1], xg[2], xg[3], true,
+            w = prod_slow_group(w, col, stride, ra[0], ra[cs], ra[2 * cs], ra[3 * cs], xg[0], xg[1], xg[2], xg[3], true,
                                 false);
         }
         unsigned status = w.st;
@@ -557,7 +526,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
                     win_add_product(w, p3, __fma_rn(a3, x3, -p3));
                     w.cnt += 4u;
                 } else {
-                    w = gemv_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
+                    w = prod_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
                     ++missed;
                 }
             }

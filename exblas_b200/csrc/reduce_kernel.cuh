@@ -23,6 +23,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "superacc.cuh"
+#include "window.cuh"
 
 namespace exb {
 
@@ -75,6 +76,7 @@ struct ReduceParams {
     int keep;                            // 1: do not reset the accumulator after publishing
     int adaptive;                        // 1: bypass the expansion while it thrashes (performance only)
     int fresh;                           // 1: the workspace accumulator is known to be zero (no pending chunks)
+    int window;                          // 1: F == 0 kernels keep a register window of the superaccumulator (performance only)
     // fused multi-GPU exchange (0 ranks = off): every rank's mailbox, mapped into this process
     Mailbox* peers[kMaxPeers];
     int nranks, rank;
@@ -359,6 +361,64 @@ EXB_D long long row_sum(unsigned row_addr, unsigned T, unsigned lane) {
     return s;
 }
 
+// ---- register window (window.cuh): the rare, out-of-line halves --------------------------------
+// Window state is passed and returned BY VALUE so that it stays in registers in the hot loops.
+// Ordinary path for one group of four columns + window bookkeeping (rare: out of line, by value so
+// that the window stays in registers in the hot loop).
+__device__ __noinline__ Window prod_slow_group(Window w, unsigned col, unsigned stride, double a0, double a1, double a2,
+                                               double a3, double x0, double x1, double x2, double x3, bool mine,
+                                               bool track) {
+    const double xa[4] = {a0, a1, a2, a3}, xb[4] = {x0, x1, x2, x3};
+    double none[1][expansions(0)];
+    unsigned status = w.st;
+    mul_add4<0, false, false>(col, stride, none, status, xa, xb);
+    if (track) {
+        unsigned hi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hi[k] = (unsigned)__double2hiint(__dmul_rn(xa[k], xb[k]));
+        win_after_slow_group<4>(w, mine, hi, false, [&](double v) { deposit(col, stride, v, status); });
+    }
+    w.st = status;
+    return w;
+}
+
+__device__ __noinline__ Window win_flush_products(Window w, unsigned col, unsigned stride) {
+    double out[4];
+    win_drain(w, out);
+    unsigned status = w.st;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (out[k] != 0.0) deposit(col, stride, out[k], status);
+    w.st = status;
+    return w;
+}
+
+// ordinary path for four single summands + window bookkeeping (rare: out of line, window by value)
+__device__ __noinline__ Window sum_slow_group(Window w, unsigned col, unsigned stride, double x0, double x1, double x2,
+                                              double x3, bool mine) {
+    unsigned status = w.st;
+    deposit(col, stride, x0, status);
+    deposit(col, stride, x1, status);
+    deposit(col, stride, x2, status);
+    deposit(col, stride, x3, status);
+    const unsigned hi[4] = {(unsigned)__double2hiint(x0), (unsigned)__double2hiint(x1), (unsigned)__double2hiint(x2),
+                            (unsigned)__double2hiint(x3)};
+    win_after_slow_group<4>(w, mine, hi, true, [&](double v) { deposit(col, stride, v, status); });
+    w.st = status;
+    return w;
+}
+
+__device__ __noinline__ Window win_flush_singles(Window w, unsigned col, unsigned stride) {
+    double out[4];
+    win_drain_single(w, out);
+    unsigned status = w.st;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (out[k] != 0.0) deposit(col, stride, out[k], status);
+    w.st = status;
+    return w;
+}
+
 // Thrash control for the expansion (performance only; the sum is exact either way).  When most
 // elements fall off the last level -- data whose dynamic range exceeds what F doubles can hold,
 // e.g. log-uniform over 2^+-332 -- the TwoSum walk is pure overhead, so the warp bypasses the
@@ -366,14 +426,15 @@ EXB_D long long row_sum(unsigned row_addr, unsigned T, unsigned lane) {
 constexpr int kBypassTiles = 32;
 constexpr int kBypassMax = 4096;
 
-template <int F, bool EE, bool DOT, int U, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReduceParams prm) {
-    extern __shared__ long long smem[];
-    const unsigned T = blockDim.x;
-    const unsigned tid = threadIdx.x;
-    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
-    const unsigned stride = 8u * T;
-    const unsigned col = smem_base + 8u * tid;
+// Everything after the vector body, shared by the streaming kernels: the scalar part (alignment head, tail, or
+// the whole strided vector), the flush of the expansions, the block merge, and the last CTA's global merge,
+// (optional) peer exchange, rounding and publication.  `body` = elements the vector body has consumed.
+template <int F, bool EE, bool DOT>
+EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsigned stride, const unsigned smem_base,
+                         const unsigned T, const unsigned tid, const long long body,
+                         double (&a)[F > 0 ? F : 1][expansions(F)], unsigned status) {
+    constexpr int kM = expansions(F);
+    constexpr int kDepPerElem = DOT ? 2 : 1;               // at most one deposit per summand
     __shared__ long long block_limbs[kLimbs];
     __shared__ unsigned is_last;
     __shared__ unsigned block_status;
@@ -382,129 +443,8 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
     const bool solo = (gridDim.x == 1) && prm.fresh && prm.finalize;
     if (tid == 0) block_status = 0;
 
-    for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
-    // columns are thread-private: no barrier needed before use
-
-    unsigned status = 0;
-    constexpr int kM = expansions(F);
-    double a[F > 0 ? F : 1][kM];
-#pragma unroll
-    for (int i = 0; i < (F > 0 ? F : 1); ++i)
-#pragma unroll
-        for (int m = 0; m < kM; ++m) a[i][m] = 0.0;
-
-    constexpr int kDepPerElem = DOT ? 2 : 1;               // at most one deposit per summand
-    constexpr int kDepPerTile = 4 * U * kDepPerElem;
-    const long long TILE = (long long)T * 4 * U;
-
-    // ---------------- vector body: full tiles, 256-bit loads, rolling prefetch ----------------
-    if (prm.ntiles > 0 && (long long)blockIdx.x < prm.ntiles) {
-        // this CTA owns tiles blockIdx.x, blockIdx.x + grid, ...: `iters` of them
-        const unsigned iters = (unsigned)((prm.ntiles - 1 - blockIdx.x) / gridDim.x) + 1u;
-        const long long tile_step = (long long)gridDim.x * TILE;               // elements between my tiles
-        const double* pa = prm.a + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4;
-        const double* pb = DOT ? prm.b + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4 : nullptr;
-        const long long vstep = (long long)T * 4;                               // elements between my vectors
-        Vec4 va[U];
-        Vec4 vb[DOT ? U : 1];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            va[u] = ldg256(pa + u * vstep);
-            if (DOT) vb[u] = ldg256(pb + u * vstep);
-        }
-        int since_norm = 0;
-        int bypass = 0, backoff = kBypassTiles;
-        for (unsigned it = 0; it < iters; ++it) {
-            pa += tile_step;
-            if (DOT) pb += tile_step;
-            const bool has_next = it + 1 < iters;
-            const bool direct = (F == 0) || (prm.adaptive && bypass > 0);
-            int deposits = 0;
-            // Two separately unrolled tile bodies (only one is hot at a time, so each fits the
-            // instruction cache): direct deposits, or the expansion walk.  Each vector slot is
-            // refilled for the next tile right after it is consumed.
-            if (direct) {
-                // ExSUM: one vote per tile on the signs of everything in the register window; an
-                // all-positive tile (the reference generator's data, norms, energies ...) takes the
-                // sign-free deposit, 7 integer instructions per element cheaper.
-                bool all_pos = false;
-#ifndef EXB_NO_POS
-                if (!DOT) {
-                    unsigned hs = 0u;
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        hs |= (unsigned)__double2hiint(va[u].x) | (unsigned)__double2hiint(va[u].y) |
-                              (unsigned)__double2hiint(va[u].z) | (unsigned)__double2hiint(va[u].w);
-                    all_pos = !__any_sync(0xffffffffu, (int)hs < 0);
-                }
-#endif
-                if (!DOT && all_pos) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        deposit4<true>(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
-                        if (has_next) va[u] = ldg256(pa + u * vstep);
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (DOT) {
-                            const double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
-                            const double y[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-                            double none[1][expansions(0)];
-                            mul_add4<0, false, true>(col, stride, none, status, x, y);
-                        } else {
-                            deposit4<false>(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
-                        }
-                        if (has_next) {
-                            va[u] = ldg256(pa + u * vstep);
-                            if (DOT) vb[u] = ldg256(pb + u * vstep);
-                        }
-                    }
-                }
-            } else if (F > 0) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
-                    if (DOT) {
-                        const double y[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-                        deposits += mul_add4<F, EE, true>(col, stride, a, status, x, y);
-                    } else {
-                        deposits += add4<F, EE, true>(col, stride, a, status, x);
-                    }
-                    if (has_next) {
-                        va[u] = ldg256(pa + u * vstep);
-                        if (DOT) vb[u] = ldg256(pb + u * vstep);
-                    }
-                }
-            }
-            if (F > 0 && prm.adaptive) {
-                if (bypass > 0) {
-                    --bypass;
-                } else {
-                    // Warp-uniform decision.  A deposit is an out-of-line, divergent call: once more than
-                    // ~1.5 % of the warp's summands need one, nearly every vector step pays for it and
-                    // depositing everything directly is cheaper.  Back off exponentially while it lasts.
-                    const int total = __reduce_add_sync(0xffffffffu, deposits);
-                    if (total * 64 >= 32 * kDepPerTile) {
-                        bypass = backoff;
-                        backoff = min(backoff * 16, kBypassMax);   // a second thrashing probe in a row: stay away for long
-                    } else {
-                        backoff = kBypassTiles;
-                    }
-                }
-            }
-            since_norm += kDepPerTile;
-            if (since_norm > kMaxDepositsPerNormalize - kDepPerTile - 2 * kM * (F + 2)) {
-                bound_column(col, stride);
-                since_norm = 0;
-            }
-        }
-        bound_column(col, stride);
-    }
-
     // ---------------- scalar part: alignment head, tail, or the whole strided vector ----------
     {
-        const long long body = prm.ntiles * TILE;
         const long long nscalar = prm.n - body;            // head + tail (or everything)
         const long long gthreads = (long long)gridDim.x * T;
         int since_norm = 0;
@@ -675,6 +615,341 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
         if (!solo && (!prm.finalize || prm.keep))
             for (unsigned j = tid; j < (unsigned)kLimbs; j += T) prm.ws->gacc[j] = (unsigned long long)block_limbs[j];
     }
+}
+
+template <int F, bool EE, bool DOT, int U, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReduceParams prm) {
+    extern __shared__ long long smem[];
+    const unsigned T = blockDim.x;
+    const unsigned tid = threadIdx.x;
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned stride = 8u * T;
+    const unsigned col = smem_base + 8u * tid;
+
+    for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+    // columns are thread-private: no barrier needed before use
+
+    unsigned status = 0;
+    constexpr int kM = expansions(F);
+    double a[F > 0 ? F : 1][kM];
+#pragma unroll
+    for (int i = 0; i < (F > 0 ? F : 1); ++i)
+#pragma unroll
+        for (int m = 0; m < kM; ++m) a[i][m] = 0.0;
+
+    constexpr int kDepPerElem = DOT ? 2 : 1;               // at most one deposit per summand
+    constexpr int kDepPerTile = 4 * U * kDepPerElem;
+    const long long TILE = (long long)T * 4 * U;
+
+    // ---------------- vector body: full tiles, 256-bit loads, rolling prefetch ----------------
+    if (prm.ntiles > 0 && (long long)blockIdx.x < prm.ntiles) {
+        // this CTA owns tiles blockIdx.x, blockIdx.x + grid, ...: `iters` of them
+        const unsigned iters = (unsigned)((prm.ntiles - 1 - blockIdx.x) / gridDim.x) + 1u;
+        const long long tile_step = (long long)gridDim.x * TILE;               // elements between my tiles
+        const double* pa = prm.a + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4;
+        const double* pb = DOT ? prm.b + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4 : nullptr;
+        const long long vstep = (long long)T * 4;                               // elements between my vectors
+        Vec4 va[U];
+        Vec4 vb[DOT ? U : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            va[u] = ldg256(pa + u * vstep);
+            if (DOT) vb[u] = ldg256(pb + u * vstep);
+        }
+        int since_norm = 0;
+        int bypass = 0, backoff = kBypassTiles;
+        for (unsigned it = 0; it < iters; ++it) {
+            pa += tile_step;
+            if (DOT) pb += tile_step;
+            const bool has_next = it + 1 < iters;
+            const bool direct = (F == 0) || (prm.adaptive && bypass > 0);
+            int deposits = 0;
+            // Two separately unrolled tile bodies (only one is hot at a time, so each fits the
+            // instruction cache): direct deposits, or the expansion walk.  Each vector slot is
+            // refilled for the next tile right after it is consumed.
+            if (direct) {
+                // ExSUM: one vote per tile on the signs of everything in the register window; an
+                // all-positive tile (the reference generator's data, norms, energies ...) takes the
+                // sign-free deposit, 7 integer instructions per element cheaper.
+                bool all_pos = false;
+#ifndef EXB_NO_POS
+                if (!DOT) {
+                    unsigned hs = 0u;
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        hs |= (unsigned)__double2hiint(va[u].x) | (unsigned)__double2hiint(va[u].y) |
+                              (unsigned)__double2hiint(va[u].z) | (unsigned)__double2hiint(va[u].w);
+                    all_pos = !__any_sync(0xffffffffu, (int)hs < 0);
+                }
+#endif
+                if (!DOT && all_pos) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        deposit4<true>(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
+                        if (has_next) va[u] = ldg256(pa + u * vstep);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (DOT) {
+                            const double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                            const double y[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+                            double none[1][expansions(0)];
+                            mul_add4<0, false, true>(col, stride, none, status, x, y);
+                        } else {
+                            deposit4<false>(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
+                        }
+                        if (has_next) {
+                            va[u] = ldg256(pa + u * vstep);
+                            if (DOT) vb[u] = ldg256(pb + u * vstep);
+                        }
+                    }
+                }
+            } else if (F > 0) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                    if (DOT) {
+                        const double y[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+                        deposits += mul_add4<F, EE, true>(col, stride, a, status, x, y);
+                    } else {
+                        deposits += add4<F, EE, true>(col, stride, a, status, x);
+                    }
+                    if (has_next) {
+                        va[u] = ldg256(pa + u * vstep);
+                        if (DOT) vb[u] = ldg256(pb + u * vstep);
+                    }
+                }
+            }
+            if (F > 0 && prm.adaptive) {
+                if (bypass > 0) {
+                    --bypass;
+                } else {
+                    // Warp-uniform decision.  A deposit is an out-of-line, divergent call: once more than
+                    // ~1.5 % of the warp's summands need one, nearly every vector step pays for it and
+                    // depositing everything directly is cheaper.  Back off exponentially while it lasts.
+                    const int total = __reduce_add_sync(0xffffffffu, deposits);
+                    if (total * 64 >= 32 * kDepPerTile) {
+                        bypass = backoff;
+                        backoff = min(backoff * 16, kBypassMax);   // a second thrashing probe in a row: stay away for long
+                    } else {
+                        backoff = kBypassTiles;
+                    }
+                }
+            }
+            since_norm += kDepPerTile;
+            if (since_norm > kMaxDepositsPerNormalize - kDepPerTile - 2 * kM * (F + 2)) {
+                bound_column(col, stride);
+                since_norm = 0;
+            }
+        }
+        bound_column(col, stride);
+    }
+
+    reduce_finish<F, EE, DOT>(prm, col, stride, smem_base, T, tid, prm.ntiles * TILE, a, status);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Superaccumulator-only streaming kernel (fpe < 2 for ExSUM, fpe < 3 for ExDOT): the reference's
+// ExSUM.Superacc.cl:212-294 / ExDOT.Superacc.cl:218-320 mode, with a register window (window.cuh) in
+// front of the shared-memory superaccumulator.
+//
+// Geometry: a ROW is T * 4 consecutive elements (one 256-bit vector per thread); this CTA owns rows
+// blockIdx, blockIdx + grid, ...  Two loops over its rows, each with its own prefetch depth, so that
+// each gets the registers it needs (a prefetch slot that spills to local memory stalls on its own
+// load and serialises the whole window -- measured: 4.3 instead of 7.2 TB/s):
+//   1. window loop, DW rows in flight: a vector whose four summands (products) lie inside the window of
+//      EVERY lane of the warp (one vote) is accumulated in registers -- 4 FP64 + 4 integer instructions
+//      per summand, 2 + 8 FP64 + 8 integer per product, no shared-memory traffic.  Any other vector
+//      takes the ordinary deposits out of line.  Two blocks of DW rows in a row that mostly miss
+//      (wide-range data such as the log-uniform benchmark vector) end this loop for good;
+//   2. direct loop, DD >= DW rows in flight: every summand is deposited (sign-free when a whole block of
+//      rows is positive, as in exblas_reduce_kernel).
+// Tail, merge and publication are reduce_finish, the same code as the expansion kernels.
+// ------------------------------------------------------------------------------------------------
+// Loop 1 of exblas_reduce0_kernel, out of line ON PURPOSE: as a separate function it gets its own register
+// allocation, so that its window state and temporaries cannot push the direct loop's prefetch slots or
+// pointers into local memory (inlined, the direct loop lost 8-12 %).  Consumes rows 0, DW, 2 DW, ... of this
+// CTA while the window holds; returns the number of rows consumed (a multiple of DW).  Rows it had in
+// flight but not consumed when it stops are simply loaded again by the caller (they come from L2).
+template <bool DOT, int DW>
+__device__ __noinline__ unsigned reduce0_window_rows(const double* pa, const double* pb, const long long row_step,
+                                                     const unsigned iters, const unsigned col, const unsigned stride,
+                                                     unsigned* status_io) {
+    constexpr int kDepPerElem = DOT ? 2 : 1;
+    Vec4 va[DW];
+    Vec4 vb[DOT ? DW : 1];
+    unsigned loaded = 0;
+    auto load_row = [&](int u) {
+        va[u] = ldg256(pa);
+        if (DOT) vb[DOT ? u : 0] = ldg256(pb);
+        pa += row_step;
+        if (DOT) pb += row_step;
+        ++loaded;
+    };
+#pragma unroll
+    for (int u = 0; u < DW; ++u)
+        if (loaded < iters) load_row(u);
+    Window w;
+    win_reset(w);
+    unsigned k = 0;
+    int since_norm = 0;
+    for (int bad = 0; k + DW <= iters && bad < 2; k += DW) {
+        int missed = 0;
+#pragma unroll
+        for (int u = 0; u < DW; ++u) {
+            const double a0 = va[u].x, a1 = va[u].y, a2 = va[u].z, a3 = va[u].w;
+            const double b0 = DOT ? vb[DOT ? u : 0].x : 0.0, b1 = DOT ? vb[DOT ? u : 0].y : 0.0;
+            const double b2 = DOT ? vb[DOT ? u : 0].z : 0.0, b3 = DOT ? vb[DOT ? u : 0].w : 0.0;
+            if (loaded < iters) load_row(u);               // row k + DW + u
+            if (DOT) {
+                const double p0 = __dmul_rn(a0, b0), p1 = __dmul_rn(a1, b1), p2 = __dmul_rn(a2, b2), p3 = __dmul_rn(a3, b3);
+                const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
+                const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
+                const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
+                const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
+                const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+                if (__all_sync(0xffffffffu, mine)) {
+                    win_add_product(w, p0, __fma_rn(a0, b0, -p0));
+                    win_add_product(w, p1, __fma_rn(a1, b1, -p1));
+                    win_add_product(w, p2, __fma_rn(a2, b2, -p2));
+                    win_add_product(w, p3, __fma_rn(a3, b3, -p3));
+                    w.cnt += 4u;
+                } else {
+                    w = prod_slow_group(w, col, stride, a0, a1, a2, a3, b0, b1, b2, b3, mine, true);
+                    ++missed;
+                }
+            } else {
+                const unsigned key = w.key0 - (1u << 20);    // single summands: exponent in [b, b + 50]
+                const unsigned span = w.span ? kWinSpanSum : 0u;
+                const unsigned k0 = ((unsigned)__double2hiint(a0) & 0x7fffffffu) - key;
+                const unsigned k1 = ((unsigned)__double2hiint(a1) & 0x7fffffffu) - key;
+                const unsigned k2 = ((unsigned)__double2hiint(a2) & 0x7fffffffu) - key;
+                const unsigned k3 = ((unsigned)__double2hiint(a3) & 0x7fffffffu) - key;
+                const bool mine = max(max(k0, k1), max(k2, k3)) < span;
+                if (__all_sync(0xffffffffu, mine)) {
+                    win_add_single(w, a0);
+                    win_add_single(w, a1);
+                    win_add_single(w, a2);
+                    win_add_single(w, a3);
+                    w.cnt += 4u;
+                } else {
+                    w = sum_slow_group(w, col, stride, a0, a1, a2, a3, mine);
+                    ++missed;
+                }
+            }
+        }
+        bad = (2 * missed > DW) ? bad + 1 : 0;              // warp-uniform: the votes are
+        if (w.cnt > (unsigned)(kWinFlushEvery - 4 * DW)) {
+            w = DOT ? win_flush_products(w, col, stride) : win_flush_singles(w, col, stride);
+            since_norm += 4;
+        }
+        since_norm += missed * (4 * kDepPerElem + 4);       // ordinary deposits + a drain when a lane re-anchors
+        if (since_norm > kMaxDepositsPerNormalize - DW * (4 * kDepPerElem + 4) - 16) {
+            bound_column(col, stride);
+            since_norm = 0;
+        }
+    }
+    w = DOT ? win_flush_products(w, col, stride) : win_flush_singles(w, col, stride);
+    *status_io |= w.st;
+    bound_column(col, stride);
+    return k;
+}
+
+template <bool DOT, int DW, int DD, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const ReduceParams prm) {
+    extern __shared__ long long smem[];
+    const unsigned T = blockDim.x;
+    const unsigned tid = threadIdx.x;
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned stride = 8u * T;
+    const unsigned col = smem_base + 8u * tid;
+    for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+
+    unsigned status = 0;
+    constexpr int kDepPerElem = DOT ? 2 : 1;
+    const long long ROW = (long long)T * 4;
+
+    if (prm.ntiles > 0 && (long long)blockIdx.x < prm.ntiles) {
+        const unsigned iters = (unsigned)((prm.ntiles - 1 - blockIdx.x) / gridDim.x) + 1u;     // my rows
+        const long long row_step = (long long)gridDim.x * ROW;
+        const double* pa = prm.a + prm.head + (long long)blockIdx.x * ROW + (long long)tid * 4;  // my first row
+        const double* pb = DOT ? prm.b + prm.head + (long long)blockIdx.x * ROW + (long long)tid * 4 : nullptr;
+        // ---------------- loop 1: register window (out of line) ----------------
+        unsigned k = 0;                                        // rows consumed so far
+        if constexpr (DW > 0) if (prm.window) {
+            unsigned st1 = 0;
+            k = reduce0_window_rows<DOT, DW>(pa, pb, row_step, iters, col, stride, &st1);
+            status |= st1;
+            pa += (long long)k * row_step;
+            if (DOT) pb += (long long)k * row_step;
+        }
+        // ---------------- loop 2: direct deposits, DD rows in flight; slot u holds row k + u ----------------
+        Vec4 va[DD];
+        Vec4 vb[DOT ? DD : 1];
+        unsigned loaded = k;                                   // rows loaded (or consumed by loop 1) so far
+        auto load_row = [&](int u) {
+            va[u] = ldg256(pa);
+            if (DOT) vb[DOT ? u : 0] = ldg256(pb);
+            pa += row_step;
+            if (DOT) pb += row_step;
+            ++loaded;
+        };
+        int since_norm = 0;
+#pragma unroll
+        for (int u = 0; u < DD; ++u)
+            if (loaded < iters) load_row(u);
+        auto consume = [&](int u, bool all_pos) {
+            if (DOT) {
+                const double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                const double y[4] = {vb[DOT ? u : 0].x, vb[DOT ? u : 0].y, vb[DOT ? u : 0].z, vb[DOT ? u : 0].w};
+                double none[1][expansions(0)];
+                mul_add4<0, false, true>(col, stride, none, status, x, y);
+            } else if (all_pos) {
+                deposit4<true>(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
+            } else {
+                deposit4<false>(col, stride, va[u].x, va[u].y, va[u].z, va[u].w, status);
+            }
+        };
+        for (; k + DD <= iters; k += DD) {
+            // ExSUM: one vote per block of rows on the signs of everything in the register window; an all-positive
+            // block (the reference generator's data, norms, energies ...) takes the sign-free deposit
+            bool all_pos = false;
+            if (!DOT) {
+                unsigned hs = 0u;
+#pragma unroll
+                for (int u = 0; u < DD; ++u)
+                    hs |= (unsigned)__double2hiint(va[u].x) | (unsigned)__double2hiint(va[u].y) |
+                          (unsigned)__double2hiint(va[u].z) | (unsigned)__double2hiint(va[u].w);
+                all_pos = !__any_sync(0xffffffffu, (int)hs < 0);
+            }
+            if (all_pos) {
+#pragma unroll
+                for (int u = 0; u < DD; ++u) {
+                    consume(u, true);
+                    if (loaded < iters) load_row(u);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < DD; ++u) {
+                    consume(u, false);
+                    if (loaded < iters) load_row(u);
+                }
+            }
+            since_norm += 4 * DD * kDepPerElem;
+            if (since_norm > kMaxDepositsPerNormalize - 8 * DD * kDepPerElem - 16) {
+                bound_column(col, stride);
+                since_norm = 0;
+            }
+        }
+        // rows left in the slots (< DD)
+#pragma unroll
+        for (int u = 0; u < DD; ++u)
+            if (k + u < iters) consume(u, false);
+        bound_column(col, stride);
+    }
+    double none[1][expansions(0)];
+    reduce_finish<0, false, DOT>(prm, col, stride, smem_base, T, tid, prm.ntiles * ROW, none, status);
 }
 
 // Multi-GPU epilogue: the result slot's limbs and flag counters have been summed over ranks by an

@@ -34,32 +34,6 @@ struct SegParams {
     int round_mode;
 };
 
-// ordinary path for four single summands + window bookkeeping (rare: out of line, window by value)
-__device__ __noinline__ Window sum_slow_group(Window w, unsigned col, unsigned stride, double x0, double x1, double x2,
-                                              double x3, bool mine) {
-    unsigned status = w.st;
-    deposit(col, stride, x0, status);
-    deposit(col, stride, x1, status);
-    deposit(col, stride, x2, status);
-    deposit(col, stride, x3, status);
-    const unsigned hi[4] = {(unsigned)__double2hiint(x0), (unsigned)__double2hiint(x1), (unsigned)__double2hiint(x2),
-                            (unsigned)__double2hiint(x3)};
-    win_after_slow_group<4>(w, mine, hi, true, [&](double v) { deposit(col, stride, v, status); });
-    w.st = status;
-    return w;
-}
-
-__device__ __noinline__ Window win_flush_singles(Window w, unsigned col, unsigned stride) {
-    double out[4];
-    win_drain_single(w, out);
-    unsigned status = w.st;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (out[k] != 0.0) deposit(col, stride, out[k], status);
-    w.st = status;
-    return w;
-}
-
 // lane 0 at the end of a segment: summed limbs -> rounded result (+ status)
 __device__ __noinline__ void segment_store(const long long* wl, unsigned st, double* out, unsigned* st_out, int round_mode,
                                            unsigned* ws_status) {
@@ -123,7 +97,7 @@ __global__ void __launch_bounds__(MAXT, 2) exblas_segments_kernel(const SegParam
                     win_add_product(w, p3, __fma_rn(a3, b3, -p3));
                     w.cnt += 4u;
                 } else {
-                    w = gemv_slow_group(w, col, stride, a0, a1, a2, a3, b0, b1, b2, b3, mine, true);
+                    w = prod_slow_group(w, col, stride, a0, a1, a2, a3, b0, b1, b2, b3, mine, true);
                     since_norm += 12;
                 }
                 if (w.cnt > (unsigned)(kWinFlushEvery - 4)) {

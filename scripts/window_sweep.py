@@ -1,0 +1,51 @@
+"""Development helper: F == 0 kernels (ExSUM / ExDOT) with the register window on / off, n = 2^30."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import exblas_b200 as xb
+from exblas_b200 import common as cm
+lg = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+n = 1 << lg
+dev = torch.device("cuda:0")
+h = xb.Handle(0)
+s = torch.cuda.Stream(); torch.cuda.set_stream(s); h.set_stream(s.cuda_stream)
+def fp(rng, emax, seed, neg=2):
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    for lo in range(0, n, 1 << 27):
+        out[lo:lo + (1 << 27)] = cm.init_fpuniform(n, rng, emax, seed=seed, neg_ratio=neg, lo=lo, hi=min(n, lo + (1 << 27)), device=dev)
+    return out
+data = {"naive": cm.init_naive(n, device=dev), "narrow": fp(10, 5, 1), "ill": cm.init_ill_cond(n, 1e32, seed=1, device=dev),
+        "logu": fp(664, 332, 1), "logupos": fp(664, 332, 1, neg=0)}
+b = fp(10, 5, 2)
+torch.cuda.synchronize()
+def timeit(fn, reps=5):
+    fn(); fn()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(reps): fn()
+    e1.record(s); e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+import json
+for op in ("exsum", "exdot"):
+    for kind, a in data.items():
+        best = {w: 1e9 for w in range(2)}
+        vals = {}
+        for rep in range(3):                      # alternate the variants so that clock drift hits all alike
+            for win in (0, 1):                    # register window off / on
+                h.set_option("window", win)
+                if op == "exsum":
+                    ms = timeit(lambda: h.exsum_async(n, a, 1, 0, 0, False))
+                else:
+                    ms = timeit(lambda: h.exdot_async(n, a, 1, 0, b, 1, 0, 0, False))
+                best[win] = min(best[win], ms)
+                vals[win] = h.fetch()[0]
+        ref3 = 1e9                                # same box, same moment: the expansion kernel (fpe 3; bypass on wide data)
+        for rep in range(2):
+            if op == "exsum":
+                ref3 = min(ref3, timeit(lambda: h.exsum_async(n, a, 1, 0, 3, False)))
+            else:
+                ref3 = min(ref3, timeit(lambda: h.exdot_async(n, a, 1, 0, b, 1, 0, 3, False)))
+        per = 8 if op == "exsum" else 16
+        print(json.dumps({"op": op, "data": kind, "fpe": 0, "GBs_plain": round(n * per / best[0] / 1e6, 1),
+                          "GBs_window": round(n * per / best[1] / 1e6, 1),
+                          "GBs_fpe3": round(n * per / ref3 / 1e6, 1), "same_bits": len(set(vals.values())) == 1}), flush=True)
