@@ -110,7 +110,7 @@ struct exblas_b200_handle_s {
     int64_t opt_gemv_parts = 0;
     int64_t opt_gemv_t_shape = 2;
     int64_t opt_gemv_n_shape = 1;
-    int64_t opt_window = 1;                 // register window in the superaccumulator-only kernels (performance only)
+    int64_t opt_window = 2;                 // register window in the superaccumulator-only kernels (performance only)
     void* comm = nullptr;
     int nranks = 1;
     // fused peer-memory exchange (exblas_b200_peer_export / peer_attach)
@@ -207,7 +207,7 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     p.round_mode = round_mode;
     p.keep = 0;
     p.adaptive = h->opt_adaptive ? 1 : 0;
-    p.window = h->opt_window ? 1 : 0;
+    p.window = (int)h->opt_window;                   // 0 off, 1 three-digit window, 2 (default) + five-digit window for ExDOT
     p.fresh = h->acc_pending ? 0 : 1;
     p.nranks = 0;
     if (finalize && h->peer_ranks > 1 && h->opt_fused) {          // closing launch: exchange limbs inside the kernel
@@ -227,7 +227,7 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
         else if (n <= (1 << 18)) { T = 128; }          // small CTAs, little shared memory to clear
     }
     // superaccumulator-only kernels (exblas_reduce0_kernel) tile by rows of T * 4 elements
-    const int U = f == 0 ? 1 : vectors_in_flight(f, ee, dot);
+    const int U = f == 0 ? 1 : vectors_in_flight(f, ee, dot);     // exblas_reduce0_kernel tiles by rows of T * 4 elements
     const int64_t tile = (int64_t)T * 4 * U;
 
     // vector body needs unit strides and, for ExDOT, the same 32-byte phase on both streams
@@ -761,7 +761,8 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
         if (value < 0 || value > 2) return EXBLAS_B200_EINVAL;
         h->opt_gemv_n_shape = value;
     } else if (!strcmp(name, "window")) {
-        h->opt_window = value != 0;
+        if (value < 0 || value > 3) return EXBLAS_B200_EINVAL;
+        h->opt_window = value;
     } else if (!strcmp(name, "adaptive")) {
         h->opt_adaptive = value != 0;
     } else if (!strcmp(name, "host_chunk_elems")) {

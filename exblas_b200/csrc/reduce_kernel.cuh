@@ -617,6 +617,10 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
     }
 }
 
+// (Measured and rejected, round 1: moving the thrash bypass or the expansion walk of THIS kernel into out-of-line
+// functions, as exblas_reduce0_kernel does with its window loop.  The expansion walk contains calls (deposits of
+// residuals), and a function that is itself called and calls on spills its prefetch slots: 1.9 instead of
+// 6.0 TB/s on narrow data; a call to an out-of-line bypass from inside this loop cost the walk 40 %.)
 template <int F, bool EE, bool DOT, int U, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReduceParams prm) {
     extern __shared__ long long smem[];
@@ -856,6 +860,203 @@ __device__ __noinline__ unsigned reduce0_window_rows(const double* pa, const dou
     return k;
 }
 
+// ---- the same loop with the W-digit product window (window.cuh, WindowP<W>): tried by ExDOT after the 3-digit
+// window gave up, for products that span more than 50 binades (W = 5: 154), e.g. ill-conditioned dot products ----
+template <int W>
+__device__ __noinline__ WindowP<W> prodw_slow_group(WindowP<W> w, unsigned col, unsigned stride, double a0, double a1, double a2,
+                                                    double a3, double x0, double x1, double x2, double x3, bool mine) {
+    const double xa[4] = {a0, a1, a2, a3}, xb[4] = {x0, x1, x2, x3};
+    double none[1][expansions(0)];
+    unsigned status = w.st;
+    mul_add4<0, false, false>(col, stride, none, status, xa, xb);
+    // exponent range of this group's products over the WHOLE warp (zeros and specials do not count): every lane
+    // re-anchors to the same window, the one that admits everything that has missed so far
+    int gmin = 4096, gmax = -4096;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int E = (int)(((unsigned)__double2hiint(__dmul_rn(xa[k], xb[k])) >> 20) & 0x7ffu);
+        if (E != 0 && E != 0x7ff) {
+            gmin = min(gmin, E - 1023);
+            gmax = max(gmax, E - 1023);
+        }
+    }
+    gmin = __reduce_min_sync(0xffffffffu, gmin);
+    gmax = __reduce_max_sync(0xffffffffu, gmax);
+    winp_cover<W>(w, gmin, gmax, [&](double v) { deposit(col, stride, v, status); });
+    (void)mine;
+    w.st = status;
+    return w;
+}
+
+template <int W>
+__device__ __noinline__ WindowP<W> winp_flush(WindowP<W> w, unsigned col, unsigned stride) {
+    double out[W + 1];
+    winp_drain(w, out);
+    unsigned status = w.st;
+#pragma unroll
+    for (int k = 0; k <= W; ++k)
+        if (out[k] != 0.0) deposit(col, stride, out[k], status);
+    w.st = status;
+    return w;
+}
+
+template <int DW, int W>
+__device__ __noinline__ unsigned reduce0_window_rows_wide(const double* pa, const double* pb, const long long row_step,
+                                                          const unsigned iters, const unsigned col, const unsigned stride,
+                                                          unsigned* status_io) {
+    Vec4 va[DW];
+    Vec4 vb[DW];
+    unsigned loaded = 0;
+    auto load_row = [&](int u) {
+        va[u] = ldg256(pa);
+        vb[u] = ldg256(pb);
+        pa += row_step;
+        pb += row_step;
+        ++loaded;
+    };
+#pragma unroll
+    for (int u = 0; u < DW; ++u)
+        if (loaded < iters) load_row(u);
+    WindowP<W> w;
+    winp_reset(w);
+    unsigned k = 0;
+    int since_norm = 0;
+    for (int bad = 0; k + DW <= iters && bad < 2; k += DW) {
+        int missed = 0;
+#pragma unroll
+        for (int u = 0; u < DW; ++u) {
+            const double a0 = va[u].x, a1 = va[u].y, a2 = va[u].z, a3 = va[u].w;
+            const double b0 = vb[u].x, b1 = vb[u].y, b2 = vb[u].z, b3 = vb[u].w;
+            if (loaded < iters) load_row(u);
+            const double p0 = __dmul_rn(a0, b0), p1 = __dmul_rn(a1, b1), p2 = __dmul_rn(a2, b2), p3 = __dmul_rn(a3, b3);
+            const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
+            const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
+            const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
+            const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
+            const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+            if (__all_sync(0xffffffffu, mine)) {
+                winp_add_product(w, p0, __fma_rn(a0, b0, -p0));
+                winp_add_product(w, p1, __fma_rn(a1, b1, -p1));
+                winp_add_product(w, p2, __fma_rn(a2, b2, -p2));
+                winp_add_product(w, p3, __fma_rn(a3, b3, -p3));
+                w.cnt += 4u;
+            } else {
+                w = prodw_slow_group<W>(w, col, stride, a0, a1, a2, a3, b0, b1, b2, b3, mine);
+                ++missed;
+            }
+        }
+        bad = (2 * missed > DW) ? bad + 1 : 0;
+        if (w.cnt > (unsigned)(kWinFlushEvery - 4 * DW)) {
+            w = winp_flush<W>(w, col, stride);
+            since_norm += W + 1;
+        }
+        since_norm += missed * (8 + W + 1);                     // ordinary deposits + a drain when a lane re-anchors
+        if (since_norm > kMaxDepositsPerNormalize - DW * (8 + W + 1) - 16) {
+            bound_column(col, stride);
+            since_norm = 0;
+        }
+    }
+    w = winp_flush<W>(w, col, stride);
+    *status_io |= w.st;
+    bound_column(col, stride);
+    return k;
+}
+
+// ---- and for ExSUM: the W-digit single-summand window (W = 3: 103 binades), tried after the two-digit window
+// gave up, e.g. on the reference's ill-conditioned generator (init_ill_cond: ~65-85 binades) ----
+template <int W>
+__device__ __noinline__ WindowP<W> sumw_slow_group(WindowP<W> w, unsigned col, unsigned stride, double x0, double x1, double x2,
+                                                   double x3) {
+    unsigned status = w.st;
+    deposit(col, stride, x0, status);
+    deposit(col, stride, x1, status);
+    deposit(col, stride, x2, status);
+    deposit(col, stride, x3, status);
+    const double xs[4] = {x0, x1, x2, x3};
+    int gmin = 4096, gmax = -4096;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int E = (int)(((unsigned)__double2hiint(xs[k]) >> 20) & 0x7ffu);
+        if (E != 0 && E != 0x7ff) {
+            gmin = min(gmin, E - 1023);
+            gmax = max(gmax, E - 1023);
+        }
+    }
+    gmin = __reduce_min_sync(0xffffffffu, gmin);
+    gmax = __reduce_max_sync(0xffffffffu, gmax);
+    wins_cover<W>(w, gmin, gmax, [&](double v) { deposit(col, stride, v, status); });
+    w.st = status;
+    return w;
+}
+
+template <int W>
+__device__ __noinline__ WindowP<W> wins_flush(WindowP<W> w, unsigned col, unsigned stride) {
+    double out[W + 1];
+    wins_drain(w, out);
+    unsigned status = w.st;
+#pragma unroll
+    for (int k = 0; k <= W; ++k)
+        if (out[k] != 0.0) deposit(col, stride, out[k], status);
+    w.st = status;
+    return w;
+}
+
+template <int DW, int W>
+__device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, const long long row_step, const unsigned iters,
+                                                              const unsigned col, const unsigned stride, unsigned* status_io) {
+    Vec4 va[DW];
+    unsigned loaded = 0;
+    auto load_row = [&](int u) {
+        va[u] = ldg256(pa);
+        pa += row_step;
+        ++loaded;
+    };
+#pragma unroll
+    for (int u = 0; u < DW; ++u)
+        if (loaded < iters) load_row(u);
+    WindowP<W> w;
+    winp_reset(w);
+    unsigned k = 0;
+    int since_norm = 0;
+    for (int bad = 0; k + DW <= iters && bad < 2; k += DW) {
+        int missed = 0;
+#pragma unroll
+        for (int u = 0; u < DW; ++u) {
+            const double a0 = va[u].x, a1 = va[u].y, a2 = va[u].z, a3 = va[u].w;
+            if (loaded < iters) load_row(u);
+            const unsigned k0 = ((unsigned)__double2hiint(a0) & 0x7fffffffu) - w.key0;
+            const unsigned k1 = ((unsigned)__double2hiint(a1) & 0x7fffffffu) - w.key0;
+            const unsigned k2 = ((unsigned)__double2hiint(a2) & 0x7fffffffu) - w.key0;
+            const unsigned k3 = ((unsigned)__double2hiint(a3) & 0x7fffffffu) - w.key0;
+            const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+            if (__all_sync(0xffffffffu, mine)) {
+                wins_add(w, a0);
+                wins_add(w, a1);
+                wins_add(w, a2);
+                wins_add(w, a3);
+                w.cnt += 4u;
+            } else {
+                w = sumw_slow_group<W>(w, col, stride, a0, a1, a2, a3);
+                ++missed;
+            }
+        }
+        bad = (2 * missed > DW) ? bad + 1 : 0;
+        if (w.cnt > (unsigned)(kWinFlushEvery - 4 * DW)) {
+            w = wins_flush<W>(w, col, stride);
+            since_norm += W + 1;
+        }
+        since_norm += missed * (4 + W + 1);
+        if (since_norm > kMaxDepositsPerNormalize - DW * (4 + W + 1) - 16) {
+            bound_column(col, stride);
+            since_norm = 0;
+        }
+    }
+    w = wins_flush<W>(w, col, stride);
+    *status_io |= w.st;
+    bound_column(col, stride);
+    return k;
+}
+
 template <bool DOT, int DW, int DD, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const ReduceParams prm) {
     extern __shared__ long long smem[];
@@ -879,8 +1080,23 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const ReducePar
         unsigned k = 0;                                        // rows consumed so far
         if constexpr (DW > 0) if (prm.window) {
             unsigned st1 = 0;
-            k = reduce0_window_rows<DOT, DW>(pa, pb, row_step, iters, col, stride, &st1);
+            if (prm.window != 3) k = reduce0_window_rows<DOT, DW>(pa, pb, row_step, iters, col, stride, &st1);
             status |= st1;
+            if constexpr (!DOT) {
+                if (k < iters && prm.window > 1) {             // summands too far apart for two digits: three (103 binades)
+                    st1 = 0;
+                    k += reduce0_window_rows_wide_sum<DW, 3>(pa + (long long)k * row_step, row_step, iters - k, col, stride, &st1);
+                    status |= st1;
+                }
+            }
+            if constexpr (DOT) {
+                if (k < iters && prm.window > 1) {             // products too far apart for three digits: five
+                    st1 = 0;
+                    k += reduce0_window_rows_wide<DW, 5>(pa + (long long)k * row_step, pb + (long long)k * row_step, row_step,
+                                                         iters - k, col, stride, &st1);
+                    status |= st1;
+                }
+            }
             pa += (long long)k * row_step;
             if (DOT) pb += (long long)k * row_step;
         }

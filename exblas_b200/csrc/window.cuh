@@ -186,4 +186,238 @@ EXB_HD void win_drain_single(Window& w, double (&out)[4]) {
     w.cnt = 0u;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// W-digit window for PRODUCTS (W >= 3): the same split carried over more digits, for data whose
+// products span more than 50 binades (e.g. the ill-conditioned dot product of BASELINE config 3:
+// factors over ~60 binades each, products over ~125).  Digits k = 0 .. W-1 count units of
+// u_k = 2^(b - 52 k); a product p with TwoProd error e is admitted when
+//        b - 52 (W - 3) + 1  <=  exponent(p)  <=  b + 50          (50 + 52 (W - 3) binades)
+// p is split over digits 0 .. W-2 and e over digits 1 .. W-1, each with the chain
+//        t_k = r + M_k;  x_k = t_k - M_k;  r = r - x_k            (last digit: t only, no remainder)
+// which is exact for the same reasons as in the 3-digit case (|r| <= u_(k-1) / 2 = 2^51 u_k going in;
+// p is a multiple of 2^(exp(p) - 52) >= u_(W-2), e of 2^(exp(p) - 105) >= u_(W-1)).
+// Cost: 2 + 2 (3 (W - 2) + 1) FP64 instructions per product (W = 5: 22) against two deposits.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+struct WindowP {
+    unsigned long long a[W];         // sums of raw bit patterns, one per digit
+    double M[W];                     // magic constants
+    unsigned key0, span, cnt, misses, st;
+    int emin, emax;                  // exponents of the products that missed so far (winp_cover)
+};
+
+template <int W>
+EXB_HD void winp_reset(WindowP<W>& w) {
+    for (int k = 0; k < W; ++k) {
+        w.a[k] = 0ull;
+        w.M[k] = 0.0;
+    }
+    w.key0 = w.span = w.cnt = w.misses = w.st = 0u;
+    w.emin = 4096;
+    w.emax = -4096;
+}
+
+// Anchor an EMPTY window so that a value with high word `hi` sits in the middle of the admitted range.
+template <int W>
+EXB_HD bool winp_anchor(WindowP<W>& w, unsigned hi) {
+    const int E = (int)((hi >> 20) & 0x7ffu);
+    if (E == 0 || E == 0x7ff) return false;
+    const int b = E - 1023 - 25 + 26 * (W - 3);                  // the admitted range is [b - 52 (W-3) + 1, b + 50]
+    if (b < -984 + 52 * (W - 1) || b > kWinBMax) return false;   // u_(W-1) and every TwoProd error stay normal
+    const unsigned long long m0 = ((unsigned long long)(unsigned)(b + 52 + 1023) << 52) | 0x0008000000000000ull;
+    for (int k = 0; k < W; ++k) {
+        w.M[k] = win_from_bits(m0 - ((unsigned long long)(52 * k) << 52));
+        w.a[k] = 0ull;
+    }
+    w.key0 = (unsigned)(b - 52 * (W - 3) + 1 + 1023) << 20;
+    w.span = (unsigned)(50 + 52 * (W - 3)) << 20;
+    w.cnt = 0u;
+    return true;
+}
+
+template <int W>
+EXB_HD bool winp_holds(const WindowP<W>& w, unsigned hi) { return ((hi & 0x7fffffffu) - w.key0) < w.span; }
+
+template <int W>
+EXB_HD void winp_add_product(WindowP<W>& w, double p, double e) {
+    double r = p;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < W - 1; ++k) {                            // p: digits 0 .. W-2
+        const double t = EXB_ADD(r, w.M[k]);
+        w.a[k] += win_bits(t);
+        if (k < W - 2) r = EXB_SUB(r, EXB_SUB(t, w.M[k]));
+    }
+    r = e;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 1; k < W; ++k) {                                // e: digits 1 .. W-1
+        const double t = EXB_ADD(r, w.M[k]);
+        w.a[k] += win_bits(t);
+        if (k < W - 1) r = EXB_SUB(r, EXB_SUB(t, w.M[k]));
+    }
+}
+
+// The window's content as W + 1 doubles whose exact sum it is, and the window emptied.
+template <int W>
+EXB_HD void winp_drain(WindowP<W>& w, double (&out)[W + 1]) {
+    for (int k = 0; k <= W; ++k) out[k] = 0.0;
+    if (w.cnt == 0u) return;
+    const unsigned long long c = w.cnt;
+    long long d[W];
+    for (int k = 0; k < W; ++k) {
+        const unsigned long long per = (k == 0 || k == W - 1) ? 1ull : 2ull;     // bit patterns added per product
+        d[k] = (long long)(w.a[k] - per * c * win_bits(w.M[k]));
+    }
+    for (int k = W - 1; k > 0; --k) {
+        d[k - 1] += d[k] >> kDigits;
+        d[k] &= kLimbMask;
+    }
+    const long long top = d[0] >> kDigits;
+    d[0] &= kLimbMask;
+    const unsigned long long e0 = (win_bits(w.M[0]) >> 52) - 52ull;             // biased exponent of u_0
+    for (int k = 0; k < W; ++k) out[k] = (double)d[k] * win_from_bits((e0 - (unsigned long long)(52 * k)) << 52);
+    out[W] = (double)top * win_from_bits((e0 + 52ull) << 52);
+    for (int k = 0; k < W; ++k) w.a[k] = 0ull;
+    w.cnt = 0u;
+}
+
+template <int W, int G, class Emit>
+EXB_HD void winp_after_slow_group(WindowP<W>& w, bool mine, const unsigned (&hi)[G], Emit&& emit) {
+    if (mine) {
+        w.misses = 0u;
+        return;
+    }
+    if (++w.misses < 2u) return;
+    double out[W + 1];
+    winp_drain(w, out);
+    for (int k = 0; k <= W; ++k)
+        if (out[k] != 0.0) emit(out[k]);
+    w.span = 0u;
+    for (int k = 0; k < G; ++k)
+        if (winp_anchor(w, hi[k])) break;
+    w.misses = 0u;
+}
+
+// Anchor an EMPTY window so that it admits every exponent in [emin, emax] (unbiased exponents of products seen so
+// far), with the slack split evenly on both sides.  False when the range does not fit or lies too close to the
+// layout edges (window left unused).
+template <int W>
+EXB_HD bool winp_anchor_range(WindowP<W>& w, int emin, int emax) {
+    constexpr int width = 50 + 52 * (W - 3);                     // admitted exponents: lo .. lo + width - 1
+    const int need = emax - emin + 1;
+    if (need > width) return false;
+    const int lo = emin - (width - need) / 2;
+    const int b = lo + 52 * (W - 3) - 1;
+    if (b < -984 + 52 * (W - 1) || b > kWinBMax) return false;
+    const unsigned long long m0 = ((unsigned long long)(unsigned)(b + 52 + 1023) << 52) | 0x0008000000000000ull;
+    for (int k = 0; k < W; ++k) {
+        w.M[k] = win_from_bits(m0 - ((unsigned long long)(52 * k) << 52));
+        w.a[k] = 0ull;
+    }
+    w.key0 = (unsigned)(lo + 1023) << 20;
+    w.span = (unsigned)width << 20;
+    w.cnt = 0u;
+    return true;
+}
+
+// admitted exponent range of an anchored window
+template <int W>
+EXB_HD int winp_lo(const WindowP<W>& w) { return (int)(w.key0 >> 20) - 1023; }
+template <int W>
+EXB_HD int winp_hi(const WindowP<W>& w) { return (int)((w.key0 + w.span) >> 20) - 1024; }
+
+// Re-anchoring policy of the W-digit window: [gmin, gmax] is the exponent range of the products of a group that did
+// not take the window path (on the device: over the whole warp, so that every lane makes the same decision and all
+// lanes' windows stay identical).  The window is moved -- drained through `emit` first -- so that it admits every
+// exponent seen in such groups so far; once that range no longer fits, the window is left unused and its loop ends.
+template <int W, class Emit>
+EXB_HD void winp_cover(WindowP<W>& w, int gmin, int gmax, Emit&& emit) {
+    if (gmin > gmax) return;                                     // only zeros / specials in the group
+    if (gmin < w.emin) w.emin = gmin;
+    if (gmax > w.emax) w.emax = gmax;
+    if (w.span != 0u && winp_lo(w) <= w.emin && w.emax <= winp_hi(w)) return;
+    double out[W + 1];
+    winp_drain(w, out);
+    for (int k = 0; k <= W; ++k)
+        if (out[k] != 0.0) emit(out[k]);
+    w.span = 0u;
+    winp_anchor_range(w, w.emin, w.emax);
+}
+
+// ---------------------------------------------------------------------------------------------
+// W-digit window for SINGLE summands (ExSUM), W >= 2, on the same WindowP<W> state: x with
+//        b - 52 (W - 2)  <=  exponent(x)  <=  b + 50          (51 + 52 (W - 2) binades; W = 3: 103)
+// is split over digits 0 .. W-1 (x is a multiple of 2^(exp(x) - 52) >= u_(W-1): the last digit has no
+// remainder): 3 (W - 1) + 1 FP64 instructions per summand, one bit pattern per digit.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+EXB_HD bool wins_anchor_range(WindowP<W>& w, int emin, int emax) {
+    constexpr int width = 51 + 52 * (W - 2);
+    const int need = emax - emin + 1;
+    if (need > width) return false;
+    const int lo = emin - (width - need) / 2;
+    const int b = lo + 52 * (W - 2);
+    if (b < -984 + 52 * (W - 1) || b > kWinBMax) return false;
+    const unsigned long long m0 = ((unsigned long long)(unsigned)(b + 52 + 1023) << 52) | 0x0008000000000000ull;
+    for (int k = 0; k < W; ++k) {
+        w.M[k] = win_from_bits(m0 - ((unsigned long long)(52 * k) << 52));
+        w.a[k] = 0ull;
+    }
+    w.key0 = (unsigned)(lo + 1023) << 20;
+    w.span = (unsigned)width << 20;
+    w.cnt = 0u;
+    return true;
+}
+
+template <int W>
+EXB_HD void wins_add(WindowP<W>& w, double x) {
+    double r = x;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < W; ++k) {
+        const double t = EXB_ADD(r, w.M[k]);
+        w.a[k] += win_bits(t);
+        if (k < W - 1) r = EXB_SUB(r, EXB_SUB(t, w.M[k]));
+    }
+}
+
+template <int W>
+EXB_HD void wins_drain(WindowP<W>& w, double (&out)[W + 1]) {
+    for (int k = 0; k <= W; ++k) out[k] = 0.0;
+    if (w.cnt == 0u) return;
+    const unsigned long long c = w.cnt;
+    long long d[W];
+    for (int k = 0; k < W; ++k) d[k] = (long long)(w.a[k] - c * win_bits(w.M[k]));
+    for (int k = W - 1; k > 0; --k) {
+        d[k - 1] += d[k] >> kDigits;
+        d[k] &= kLimbMask;
+    }
+    const long long top = d[0] >> kDigits;
+    d[0] &= kLimbMask;
+    const unsigned long long e0 = (win_bits(w.M[0]) >> 52) - 52ull;
+    for (int k = 0; k < W; ++k) out[k] = (double)d[k] * win_from_bits((e0 - (unsigned long long)(52 * k)) << 52);
+    out[W] = (double)top * win_from_bits((e0 + 52ull) << 52);
+    for (int k = 0; k < W; ++k) w.a[k] = 0ull;
+    w.cnt = 0u;
+}
+
+template <int W, class Emit>
+EXB_HD void wins_cover(WindowP<W>& w, int gmin, int gmax, Emit&& emit) {
+    if (gmin > gmax) return;
+    if (gmin < w.emin) w.emin = gmin;
+    if (gmax > w.emax) w.emax = gmax;
+    if (w.span != 0u && winp_lo(w) <= w.emin && w.emax <= winp_hi(w)) return;
+    double out[W + 1];
+    wins_drain(w, out);
+    for (int k = 0; k <= W; ++k)
+        if (out[k] != 0.0) emit(out[k]);
+    w.span = 0u;
+    wins_anchor_range(w, w.emin, w.emax);
+}
+
 }  // namespace exb

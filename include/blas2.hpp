@@ -1,7 +1,7 @@
 /*
  * blas2.hpp -- drop-in replacement for the reference's include/blas2.hpp, ExGEMV only
- * (reference include/blas2.hpp:95).  transa == 'N' is implemented (BASELINE config 5); 'T' and
- * extrsv() are not part of this hot path.
+ * (reference include/blas2.hpp:95).  transa == 'N' (BASELINE config 5) and 'T'; extrsv() is not part
+ * of this hot path.
  *
  * y := alpha*A*x + beta*y with every element the rounded exact value.  A is column-major, m x n,
  * leading dimension lda.  Pointers may be host (as in the reference) or device pointers.

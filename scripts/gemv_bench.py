@@ -44,9 +44,10 @@ for kind in kinds:
     torch.cuda.synchronize()
     for trans in transs:
         ref = None
-        for label, fpe, ee, opts in [("fpe0 window", 0, False, {"window": 1}), ("fpe0 plain", 0, False, {"window": 0}),
-                                     ("fpe3", 3, False, {"window": 1}), ("fpe8ee", 8, True, {"window": 1})] + \
-                                    ([("fpe0 window shape1", 0, False, {"window": 1, "gemv_t_shape": 1})] if trans == "T" else []):
+        for label, fpe, ee, opts in [("fpe0 window", 0, False, {"window": 2}), ("fpe0 plain", 0, False, {"window": 0}),
+                                     ("fpe3", 3, False, {"window": 2}), ("fpe8ee", 8, True, {"window": 2})] + \
+                                    ([("fpe0 window 384 threads", 0, False, {"window": 2, "gemv_t_shape": 1})] if trans == "T" else
+                                     [("fpe0 window 384 threads", 0, False, {"window": 2, "gemv_n_shape": 0})]):
             for k, v in opts.items(): h.set_option(k, v)
             ms, y = timed(trans, fpe, ee)
             same = True if ref is None else bool((y.view(torch.int64) == ref.view(torch.int64)).all())
@@ -54,4 +55,4 @@ for kind in kinds:
             print(json.dumps({"op": "exgemv " + trans, "m": m, "n": n, "data": kind, "variant": label, "ms": round(ms, 3),
                               "GBs": round((m * n + m + n) * 8 / ms / 1e6, 1), "GFLOPs": round(2 * m * n / ms / 1e6, 1),
                               "bit_identical_to_first": same, "y0": float(y[0]), "status": h.last_status()}), flush=True)
-        h.set_option("window", 1); h.set_option("gemv_t_shape", 0)
+        h.set_option("window", 2); h.set_option("gemv_t_shape", 2); h.set_option("gemv_n_shape", 1)

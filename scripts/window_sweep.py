@@ -17,6 +17,7 @@ def fp(rng, emax, seed, neg=2):
 data = {"naive": cm.init_naive(n, device=dev), "narrow": fp(10, 5, 1), "ill": cm.init_ill_cond(n, 1e32, seed=1, device=dev),
         "logu": fp(664, 332, 1), "logupos": fp(664, 332, 1, neg=0)}
 b = fp(10, 5, 2)
+b_ill = cm.init_ill_cond(n, 1e32, seed=2, device=dev)
 torch.cuda.synchronize()
 def timeit(fn, reps=5):
     fn(); fn()
@@ -26,17 +27,21 @@ def timeit(fn, reps=5):
     e1.record(s); e1.synchronize()
     return e0.elapsed_time(e1) / reps
 import json
-for op in ("exsum", "exdot"):
-    for kind, a in data.items():
-        best = {w: 1e9 for w in range(2)}
+cases = [("exsum", k, v, None) for k, v in data.items()] + [("exdot", k, v, b) for k, v in data.items()] + \
+        [("exdot", "ill x ill (BASELINE config 3)", data["ill"], b_ill)]
+xa, xb_ = cm.cancelling_pair(n, "dot", seed=7, device=dev)
+cases.append(("exdot", "cancelling pairs (bench extras)", xa, xb_))
+for op, kind, a, bb in cases:
+    if True:
+        best = {w: 1e9 for w in range(4)}
         vals = {}
         for rep in range(3):                      # alternate the variants so that clock drift hits all alike
-            for win in (0, 1):                    # register window off / on
+            for win in (0, 1, 2, 3):              # register window off / narrow only / narrow then wide / wide only
                 h.set_option("window", win)
                 if op == "exsum":
                     ms = timeit(lambda: h.exsum_async(n, a, 1, 0, 0, False))
                 else:
-                    ms = timeit(lambda: h.exdot_async(n, a, 1, 0, b, 1, 0, 0, False))
+                    ms = timeit(lambda: h.exdot_async(n, a, 1, 0, bb, 1, 0, 0, False))
                 best[win] = min(best[win], ms)
                 vals[win] = h.fetch()[0]
         ref3 = 1e9                                # same box, same moment: the expansion kernel (fpe 3; bypass on wide data)
@@ -44,8 +49,8 @@ for op in ("exsum", "exdot"):
             if op == "exsum":
                 ref3 = min(ref3, timeit(lambda: h.exsum_async(n, a, 1, 0, 3, False)))
             else:
-                ref3 = min(ref3, timeit(lambda: h.exdot_async(n, a, 1, 0, b, 1, 0, 3, False)))
+                ref3 = min(ref3, timeit(lambda: h.exdot_async(n, a, 1, 0, bb, 1, 0, 3, False)))
         per = 8 if op == "exsum" else 16
         print(json.dumps({"op": op, "data": kind, "fpe": 0, "GBs_plain": round(n * per / best[0] / 1e6, 1),
-                          "GBs_window": round(n * per / best[1] / 1e6, 1),
+                          "GBs_window3": round(n * per / best[1] / 1e6, 1), "GBs_window3+5": round(n * per / best[2] / 1e6, 1), "GBs_wide_only": round(n * per / best[3] / 1e6, 1),
                           "GBs_fpe3": round(n * per / ref3 / 1e6, 1), "same_bits": len(set(vals.values())) == 1}), flush=True)

@@ -195,14 +195,14 @@ def test_exgemv_n_window_kernel(gpu, oracle):
         xbuf = np.full(3 * n, 9.0)
         xbuf[1::3][:n] = x[:n]
         want = oracle.exgemv("N", m, n, 1.0, a, lda, x[:n], 1, 1.0, y[:m], 1, 0, False, 0)
-        gpu.set_option("window", 1)
+        gpu.set_option("window", 2)
         for parts in (1, 2, 7, 40):
             gpu.set_option("gemv_parts", parts)
             dy = torch.from_numpy(y[:m].copy()).cuda()
             xb.exgemv("N", m, n, 1.0, torch.from_numpy(a).cuda(), lda, 0, torch.from_numpy(xbuf).cuda(), 3, 1, 1.0, dy, 1, 0, 0, False, handle=gpu)
             assert (dy.cpu().numpy().view(np.uint64) == want.view(np.uint64)).all(), parts
     finally:
-        gpu.set_option("window", 1)
+        gpu.set_option("window", 2)
         gpu.set_option("gemv_parts", 0)
         gpu.set_option("gemv_n_shape", 1)
 

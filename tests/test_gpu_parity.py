@@ -289,3 +289,34 @@ int main() {
     s = oracle.exsum(a, fpe=0)[0]
     d = oracle.exdot(a, b, fpe=0)[0]
     assert [float.fromhex(x) for x in out] == [s, s, s, d, d]
+
+
+def test_superacc_only_window_variants(gpu, oracle):
+    """fpe 0 (superaccumulator-only kernel): the register windows -- off, narrow only, narrow then wide, wide only --
+    must all give the oracle's value AND limbs, on data that stays in the narrow window, needs the wide one,
+    drifts so that the windows must follow, or fits neither."""
+    n = (1 << 24) + 37                      # ~55 rows of 2048 per CTA: every loop of the kernel runs, plus a ragged tail
+    rng = np.random.default_rng(3)
+    narrow = cm.init_fpuniform(n, 10, 5, seed=1, neg_ratio=2)
+    ill = cm.init_ill_cond(n, 1e32, seed=2)
+    ill2 = cm.init_ill_cond(n, 1e32, seed=3)
+    drift = narrow * np.exp2((np.arange(n) // (1 << 19)).astype(np.float64) * 9.0 - 100.0)   # moves 9 binades every 2^19 elements
+    wide = cm.init_fpuniform(n, 664, 332, seed=4, neg_ratio=2)
+    spiky = narrow.copy()
+    spiky[rng.integers(0, n, size=200)] *= 2.0 ** 300                                        # rare far outliers
+    spiky[rng.integers(0, n, size=200)] = 0.0
+    try:
+        for name, a, b in (("narrow", narrow, narrow[::-1].copy()), ("ill", ill, narrow), ("ill x ill", ill, ill2), ("drift", drift, narrow),
+                           ("wide", wide, narrow), ("spiky", spiky, ill)):
+            vs, ls = oracle.exsum(a, fpe=0, round_mode=0)
+            vd, ld = oracle.exdot(a, b, fpe=0, round_mode=0)
+            da, db = dev(a), dev(b)
+            for window in (0, 1, 2, 3):
+                gpu.set_option("window", window)
+                v, l = gpu.exsum(n, da, 1, 0, 0, False, want_limbs=True)
+                assert same_double(v, vs) and (l == ls).all(), ("exsum", name, window)
+                v, l = gpu.exdot(n, da, 1, 0, db, 1, 0, 0, False, want_limbs=True)
+                assert same_double(v, vd) and (l == ld).all(), ("exdot", name, window)
+                assert gpu.last_status() == 0
+    finally:
+        gpu.set_option("window", 2)
