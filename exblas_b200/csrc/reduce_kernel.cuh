@@ -771,97 +771,18 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
 //      rows is positive, as in exblas_reduce_kernel).
 // Tail, merge and publication are reduce_finish, the same code as the expansion kernels.
 // ------------------------------------------------------------------------------------------------
-// Loop 1 of exblas_reduce0_kernel, out of line ON PURPOSE: as a separate function it gets its own register
-// allocation, so that its window state and temporaries cannot push the direct loop's prefetch slots or
-// pointers into local memory (inlined, the direct loop lost 8-12 %).  Consumes rows 0, DW, 2 DW, ... of this
-// CTA while the window holds; returns the number of rows consumed (a multiple of DW).  Rows it had in
-// flight but not consumed when it stops are simply loaded again by the caller (they come from L2).
-template <bool DOT, int DW>
-__device__ __noinline__ unsigned reduce0_window_rows(const double* pa, const double* pb, const long long row_step,
-                                                     const unsigned iters, const unsigned col, const unsigned stride,
-                                                     unsigned* status_io) {
-    constexpr int kDepPerElem = DOT ? 2 : 1;
-    Vec4 va[DW];
-    Vec4 vb[DOT ? DW : 1];
-    unsigned loaded = 0;
-    auto load_row = [&](int u) {
-        va[u] = ldg256(pa);
-        if (DOT) vb[DOT ? u : 0] = ldg256(pb);
-        pa += row_step;
-        if (DOT) pb += row_step;
-        ++loaded;
-    };
-#pragma unroll
-    for (int u = 0; u < DW; ++u)
-        if (loaded < iters) load_row(u);
-    Window w;
-    win_reset(w);
-    unsigned k = 0;
-    int since_norm = 0;
-    for (int bad = 0; k + DW <= iters && bad < 2; k += DW) {
-        int missed = 0;
-#pragma unroll
-        for (int u = 0; u < DW; ++u) {
-            const double a0 = va[u].x, a1 = va[u].y, a2 = va[u].z, a3 = va[u].w;
-            const double b0 = DOT ? vb[DOT ? u : 0].x : 0.0, b1 = DOT ? vb[DOT ? u : 0].y : 0.0;
-            const double b2 = DOT ? vb[DOT ? u : 0].z : 0.0, b3 = DOT ? vb[DOT ? u : 0].w : 0.0;
-            if (loaded < iters) load_row(u);               // row k + DW + u
-            if (DOT) {
-                const double p0 = __dmul_rn(a0, b0), p1 = __dmul_rn(a1, b1), p2 = __dmul_rn(a2, b2), p3 = __dmul_rn(a3, b3);
-                const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
-                const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
-                const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
-                const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
-                const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
-                if (__all_sync(0xffffffffu, mine)) {
-                    win_add_product(w, p0, __fma_rn(a0, b0, -p0));
-                    win_add_product(w, p1, __fma_rn(a1, b1, -p1));
-                    win_add_product(w, p2, __fma_rn(a2, b2, -p2));
-                    win_add_product(w, p3, __fma_rn(a3, b3, -p3));
-                    w.cnt += 4u;
-                } else {
-                    w = prod_slow_group(w, col, stride, a0, a1, a2, a3, b0, b1, b2, b3, mine, true);
-                    ++missed;
-                }
-            } else {
-                const unsigned key = w.key0 - (1u << 20);    // single summands: exponent in [b, b + 50]
-                const unsigned span = w.span ? kWinSpanSum : 0u;
-                const unsigned k0 = ((unsigned)__double2hiint(a0) & 0x7fffffffu) - key;
-                const unsigned k1 = ((unsigned)__double2hiint(a1) & 0x7fffffffu) - key;
-                const unsigned k2 = ((unsigned)__double2hiint(a2) & 0x7fffffffu) - key;
-                const unsigned k3 = ((unsigned)__double2hiint(a3) & 0x7fffffffu) - key;
-                const bool mine = max(max(k0, k1), max(k2, k3)) < span;
-                if (__all_sync(0xffffffffu, mine)) {
-                    win_add_single(w, a0);
-                    win_add_single(w, a1);
-                    win_add_single(w, a2);
-                    win_add_single(w, a3);
-                    w.cnt += 4u;
-                } else {
-                    w = sum_slow_group(w, col, stride, a0, a1, a2, a3, mine);
-                    ++missed;
-                }
-            }
-        }
-        bad = (2 * missed > DW) ? bad + 1 : 0;              // warp-uniform: the votes are
-        if (w.cnt > (unsigned)(kWinFlushEvery - 4 * DW)) {
-            w = DOT ? win_flush_products(w, col, stride) : win_flush_singles(w, col, stride);
-            since_norm += 4;
-        }
-        since_norm += missed * (4 * kDepPerElem + 4);       // ordinary deposits + a drain when a lane re-anchors
-        if (since_norm > kMaxDepositsPerNormalize - DW * (4 * kDepPerElem + 4) - 16) {
-            bound_column(col, stride);
-            since_norm = 0;
-        }
-    }
-    w = DOT ? win_flush_products(w, col, stride) : win_flush_singles(w, col, stride);
-    *status_io |= w.st;
-    bound_column(col, stride);
-    return k;
-}
+// Loop 1 of exblas_reduce0_kernel, out of line ON PURPOSE: as separate functions the window loops get their own
+// register allocation, so that their window state and temporaries cannot push the direct loop's prefetch slots or
+// pointers into local memory (inlined, the direct loop lost 8-12 %).  Each consumes rows 0, DW, 2 DW, ... of this
+// CTA while its window holds and returns the number of rows consumed (a multiple of DW).  Rows it had in flight
+// but not consumed when it stops are simply loaded again by the caller (they come from L2).
+// The windows are the W-digit ones of window.cuh with the WARP-UNIFORM, range-covering anchoring: a vector that
+// misses moves every lane's window so that it admits all exponents that have missed so far; [emin, emax] travels
+// from one attempt to the next, so that a warp whose data cannot fit (log-uniform 2^+-332: the first vector
+// already spans more than any window) leaves after ONE row and skips the wider attempt altogether.
 
-// ---- the same loop with the W-digit product window (window.cuh, WindowP<W>): tried by ExDOT after the 3-digit
-// window gave up, for products that span more than 50 binades (W = 5: 154), e.g. ill-conditioned dot products ----
+// ---- ExDOT: W-digit product window (WindowP<W>): W = 3 (50 binades, 10 FP64 instructions per product) first,
+// then W = 5 (154 binades, 22) for products further apart, e.g. ill-conditioned dot products ----
 template <int W>
 __device__ __noinline__ WindowP<W> prodw_slow_group(WindowP<W> w, unsigned col, unsigned stride, double a0, double a1, double a2,
                                                     double a3, double x0, double x1, double x2, double x3, bool mine) {
@@ -900,10 +821,11 @@ __device__ __noinline__ WindowP<W> winp_flush(WindowP<W> w, unsigned col, unsign
     return w;
 }
 
-template <int DW, int W>
+template <int DW, int W, bool EARLY = false>
 __device__ __noinline__ unsigned reduce0_window_rows_wide(const double* pa, const double* pb, const long long row_step,
                                                           const unsigned iters, const unsigned col, const unsigned stride,
-                                                          unsigned* status_io) {
+                                                          unsigned* status_io, int* range_io) {
+    if (range_io[1] - range_io[0] + 1 > 50 + 52 * (W - 3)) return 0u;     // what has missed so far cannot fit this window
     Vec4 va[DW];
     Vec4 vb[DW];
     unsigned loaded = 0;
@@ -919,6 +841,8 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide(const double* pa, cons
         if (loaded < iters) load_row(u);
     WindowP<W> w;
     winp_reset(w);
+    w.emin = range_io[0];
+    w.emax = range_io[1];
     unsigned k = 0;
     int since_norm = 0;
     for (int bad = 0; k + DW <= iters && bad < 2; k += DW) {
@@ -927,30 +851,56 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide(const double* pa, cons
         for (int u = 0; u < DW; ++u) {
             const double a0 = va[u].x, a1 = va[u].y, a2 = va[u].z, a3 = va[u].w;
             const double b0 = vb[u].x, b1 = vb[u].y, b2 = vb[u].z, b3 = vb[u].w;
-            if (loaded < iters) load_row(u);
+            if (EARLY && loaded < iters) load_row(u);
             const double p0 = __dmul_rn(a0, b0), p1 = __dmul_rn(a1, b1), p2 = __dmul_rn(a2, b2), p3 = __dmul_rn(a3, b3);
             const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
             const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
             const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
             const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
-            const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
-            if (__all_sync(0xffffffffu, mine)) {
-                winp_add_product(w, p0, __fma_rn(a0, b0, -p0));
-                winp_add_product(w, p1, __fma_rn(a1, b1, -p1));
-                winp_add_product(w, p2, __fma_rn(a2, b2, -p2));
-                winp_add_product(w, p3, __fma_rn(a3, b3, -p3));
-                w.cnt += 4u;
+            if constexpr (W >= 5) {
+                // two products per vote: the temporaries of four interleaved 22-instruction splits + the 5-digit state do
+                // not fit 128 registers, and what spills is a prefetch slot (which then stalls on its own load)
+                const bool mine01 = max(k0, k1) < w.span, mine23 = max(k2, k3) < w.span;
+                if (__all_sync(0xffffffffu, mine01)) {
+                    winp_add_product(w, p0, __fma_rn(a0, b0, -p0));
+                    winp_add_product(w, p1, __fma_rn(a1, b1, -p1));
+                    w.cnt += 2u;
+                } else {
+                    w = prodw_slow_group<W>(w, col, stride, a0, a1, 0.0, 0.0, b0, b1, 0.0, 0.0, mine01);
+                    ++missed;
+                }
+                if (__all_sync(0xffffffffu, mine23)) {
+                    winp_add_product(w, p2, __fma_rn(a2, b2, -p2));
+                    winp_add_product(w, p3, __fma_rn(a3, b3, -p3));
+                    w.cnt += 2u;
+                } else {
+                    w = prodw_slow_group<W>(w, col, stride, a2, a3, 0.0, 0.0, b2, b3, 0.0, 0.0, mine23);
+                    ++missed;
+                }
             } else {
-                w = prodw_slow_group<W>(w, col, stride, a0, a1, a2, a3, b0, b1, b2, b3, mine);
-                ++missed;
+                const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+                if (__all_sync(0xffffffffu, mine)) {
+                    winp_add_product(w, p0, __fma_rn(a0, b0, -p0));
+                    winp_add_product(w, p1, __fma_rn(a1, b1, -p1));
+                    winp_add_product(w, p2, __fma_rn(a2, b2, -p2));
+                    winp_add_product(w, p3, __fma_rn(a3, b3, -p3));
+                    w.cnt += 4u;
+                } else {
+                    w = prodw_slow_group<W>(w, col, stride, a0, a1, a2, a3, b0, b1, b2, b3, mine);
+                    missed += 2;
+                }
             }
+            // the slot is refilled AFTER its row has been consumed: its registers are free by then, which keeps the
+            // W = 5 window (27 registers of state) from pushing a load in flight into local memory
+            if (!EARLY && loaded < iters) load_row(u);          // row k + DW + u
         }
-        bad = (2 * missed > DW) ? bad + 1 : 0;
+        bad = (missed > DW) ? bad + 1 : 0;                      // `missed` counts half rows here
+        if (w.span == 0u) bad = 2;                              // what has missed no longer fits the window (warp-uniform): leave
         if (w.cnt > (unsigned)(kWinFlushEvery - 4 * DW)) {
             w = winp_flush<W>(w, col, stride);
             since_norm += W + 1;
         }
-        since_norm += missed * (8 + W + 1);                     // ordinary deposits + a drain when a lane re-anchors
+        since_norm += missed * (8 + W + 1);                     // ordinary deposits + a drain when the window moves
         if (since_norm > kMaxDepositsPerNormalize - DW * (8 + W + 1) - 16) {
             bound_column(col, stride);
             since_norm = 0;
@@ -958,12 +908,14 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide(const double* pa, cons
     }
     w = winp_flush<W>(w, col, stride);
     *status_io |= w.st;
+    range_io[0] = w.emin;
+    range_io[1] = w.emax;
     bound_column(col, stride);
     return k;
 }
 
-// ---- and for ExSUM: the W-digit single-summand window (W = 3: 103 binades), tried after the two-digit window
-// gave up, e.g. on the reference's ill-conditioned generator (init_ill_cond: ~65-85 binades) ----
+// ---- ExSUM: W-digit single-summand window: W = 2 (51 binades, 4 FP64 instructions per summand) first, then
+// W = 3 (103 binades, 7), e.g. for the reference's ill-conditioned generator (init_ill_cond: ~65-85 binades) ----
 template <int W>
 __device__ __noinline__ WindowP<W> sumw_slow_group(WindowP<W> w, unsigned col, unsigned stride, double x0, double x1, double x2,
                                                    double x3) {
@@ -1003,7 +955,9 @@ __device__ __noinline__ WindowP<W> wins_flush(WindowP<W> w, unsigned col, unsign
 
 template <int DW, int W>
 __device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, const long long row_step, const unsigned iters,
-                                                              const unsigned col, const unsigned stride, unsigned* status_io) {
+                                                              const unsigned col, const unsigned stride, unsigned* status_io,
+                                                              int* range_io) {
+    if (range_io[1] - range_io[0] + 1 > 51 + 52 * (W - 2)) return 0u;
     Vec4 va[DW];
     unsigned loaded = 0;
     auto load_row = [&](int u) {
@@ -1016,6 +970,8 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, 
         if (loaded < iters) load_row(u);
     WindowP<W> w;
     winp_reset(w);
+    w.emin = range_io[0];
+    w.emax = range_io[1];
     unsigned k = 0;
     int since_norm = 0;
     for (int bad = 0; k + DW <= iters && bad < 2; k += DW) {
@@ -1023,7 +979,6 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, 
 #pragma unroll
         for (int u = 0; u < DW; ++u) {
             const double a0 = va[u].x, a1 = va[u].y, a2 = va[u].z, a3 = va[u].w;
-            if (loaded < iters) load_row(u);
             const unsigned k0 = ((unsigned)__double2hiint(a0) & 0x7fffffffu) - w.key0;
             const unsigned k1 = ((unsigned)__double2hiint(a1) & 0x7fffffffu) - w.key0;
             const unsigned k2 = ((unsigned)__double2hiint(a2) & 0x7fffffffu) - w.key0;
@@ -1039,8 +994,10 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, 
                 w = sumw_slow_group<W>(w, col, stride, a0, a1, a2, a3);
                 ++missed;
             }
+            if (loaded < iters) load_row(u);                    // row k + DW + u (after the slot has been consumed)
         }
         bad = (2 * missed > DW) ? bad + 1 : 0;
+        if (w.span == 0u) bad = 2;
         if (w.cnt > (unsigned)(kWinFlushEvery - 4 * DW)) {
             w = wins_flush<W>(w, col, stride);
             since_norm += W + 1;
@@ -1053,6 +1010,8 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, 
     }
     w = wins_flush<W>(w, col, stride);
     *status_io |= w.st;
+    range_io[0] = w.emin;
+    range_io[1] = w.emax;
     bound_column(col, stride);
     return k;
 }
@@ -1078,25 +1037,25 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const ReducePar
         const double* pb = DOT ? prm.b + prm.head + (long long)blockIdx.x * ROW + (long long)tid * 4 : nullptr;
         // ---------------- loop 1: register window (out of line) ----------------
         unsigned k = 0;                                        // rows consumed so far
-        if constexpr (DW > 0) if (prm.window) {
+        // (vectors too short for the windows to pay -- fewer than 32 rows per CTA, n < ~2^23 -- go straight to loop 2)
+        if constexpr (DW > 0) if (prm.window && iters >= 32u) {
             unsigned st1 = 0;
-            if (prm.window != 3) k = reduce0_window_rows<DOT, DW>(pa, pb, row_step, iters, col, stride, &st1);
-            status |= st1;
-            if constexpr (!DOT) {
-                if (k < iters && prm.window > 1) {             // summands too far apart for two digits: three (103 binades)
-                    st1 = 0;
-                    k += reduce0_window_rows_wide_sum<DW, 3>(pa + (long long)k * row_step, row_step, iters - k, col, stride, &st1);
-                    status |= st1;
-                }
-            }
+            int range[2] = {4096, -4096};                      // exponents that have missed so far, warp-uniform
             if constexpr (DOT) {
-                if (k < iters && prm.window > 1) {             // products too far apart for three digits: five
-                    st1 = 0;
-                    k += reduce0_window_rows_wide<DW, 5>(pa + (long long)k * row_step, pb + (long long)k * row_step, row_step,
-                                                         iters - k, col, stride, &st1);
-                    status |= st1;
-                }
+                if (prm.window != 3)
+                    k = reduce0_window_rows_wide<DW, 3>(pa, pb, row_step, iters, col, stride, &st1, range);
+                if (k < iters && prm.window > 1)
+                    // (two rows in flight, refilled BEFORE the row is consumed: measured best of 2 / 3 / 4 rows, early / late
+                    // refill: 6.7 against 5.0-6.4 TB/s on ill-conditioned data; the wide loop spends ~45 instructions per product)
+                    k += reduce0_window_rows_wide<DW, 5, true>(pa + (long long)k * row_step, pb + (long long)k * row_step, row_step,
+                                                               iters - k, col, stride, &st1, range);
+            } else {
+                if (prm.window != 3)
+                    k = reduce0_window_rows_wide_sum<DW, 2>(pa, row_step, iters, col, stride, &st1, range);
+                if (k < iters && prm.window > 1)
+                    k += reduce0_window_rows_wide_sum<DW + 2, 3>(pa + (long long)k * row_step, row_step, iters - k, col, stride, &st1, range);
             }
+            status |= st1;
             pa += (long long)k * row_step;
             if (DOT) pb += (long long)k * row_step;
         }

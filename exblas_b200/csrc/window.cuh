@@ -202,17 +202,26 @@ EXB_HD void win_drain_single(Window& w, double (&out)[4]) {
 template <int W>
 struct WindowP {
     unsigned long long a[W];         // sums of raw bit patterns, one per digit
-    double M[W];                     // magic constants
+    double M0;                       // magic constant of digit 0; M_k = M0 / 2^(52 k) is one integer subtract away (winp_M)
     unsigned key0, span, cnt, misses, st;
     int emin, emax;                  // exponents of the products that missed so far (winp_cover)
 };
 
+// magic constant of digit k: the exponent field of M0 lowered by 52 k (the low word of 1.5 * 2^e is zero).  Kept out of
+// the window state on purpose: five constants in registers made the 5-digit loop spill its prefetch slots.
+template <int W>
+EXB_HD double winp_M(const WindowP<W>& w, int k) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(w.M0) - k * (52 << 20), 0);
+#else
+    return win_from_bits(win_bits(w.M0) - ((unsigned long long)(52 * k) << 52));
+#endif
+}
+
 template <int W>
 EXB_HD void winp_reset(WindowP<W>& w) {
-    for (int k = 0; k < W; ++k) {
-        w.a[k] = 0ull;
-        w.M[k] = 0.0;
-    }
+    for (int k = 0; k < W; ++k) w.a[k] = 0ull;
+    w.M0 = 0.0;
     w.key0 = w.span = w.cnt = w.misses = w.st = 0u;
     w.emin = 4096;
     w.emax = -4096;
@@ -226,10 +235,8 @@ EXB_HD bool winp_anchor(WindowP<W>& w, unsigned hi) {
     const int b = E - 1023 - 25 + 26 * (W - 3);                  // the admitted range is [b - 52 (W-3) + 1, b + 50]
     if (b < -984 + 52 * (W - 1) || b > kWinBMax) return false;   // u_(W-1) and every TwoProd error stay normal
     const unsigned long long m0 = ((unsigned long long)(unsigned)(b + 52 + 1023) << 52) | 0x0008000000000000ull;
-    for (int k = 0; k < W; ++k) {
-        w.M[k] = win_from_bits(m0 - ((unsigned long long)(52 * k) << 52));
-        w.a[k] = 0ull;
-    }
+    w.M0 = win_from_bits(m0);
+    for (int k = 0; k < W; ++k) w.a[k] = 0ull;
     w.key0 = (unsigned)(b - 52 * (W - 3) + 1 + 1023) << 20;
     w.span = (unsigned)(50 + 52 * (W - 3)) << 20;
     w.cnt = 0u;
@@ -246,18 +253,18 @@ EXB_HD void winp_add_product(WindowP<W>& w, double p, double e) {
 #pragma unroll
 #endif
     for (int k = 0; k < W - 1; ++k) {                            // p: digits 0 .. W-2
-        const double t = EXB_ADD(r, w.M[k]);
+        const double t = EXB_ADD(r, winp_M(w, k));
         w.a[k] += win_bits(t);
-        if (k < W - 2) r = EXB_SUB(r, EXB_SUB(t, w.M[k]));
+        if (k < W - 2) r = EXB_SUB(r, EXB_SUB(t, winp_M(w, k)));
     }
     r = e;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int k = 1; k < W; ++k) {                                // e: digits 1 .. W-1
-        const double t = EXB_ADD(r, w.M[k]);
+        const double t = EXB_ADD(r, winp_M(w, k));
         w.a[k] += win_bits(t);
-        if (k < W - 1) r = EXB_SUB(r, EXB_SUB(t, w.M[k]));
+        if (k < W - 1) r = EXB_SUB(r, EXB_SUB(t, winp_M(w, k)));
     }
 }
 
@@ -270,7 +277,7 @@ EXB_HD void winp_drain(WindowP<W>& w, double (&out)[W + 1]) {
     long long d[W];
     for (int k = 0; k < W; ++k) {
         const unsigned long long per = (k == 0 || k == W - 1) ? 1ull : 2ull;     // bit patterns added per product
-        d[k] = (long long)(w.a[k] - per * c * win_bits(w.M[k]));
+        d[k] = (long long)(w.a[k] - per * c * win_bits(winp_M(w, k)));
     }
     for (int k = W - 1; k > 0; --k) {
         d[k - 1] += d[k] >> kDigits;
@@ -278,7 +285,7 @@ EXB_HD void winp_drain(WindowP<W>& w, double (&out)[W + 1]) {
     }
     const long long top = d[0] >> kDigits;
     d[0] &= kLimbMask;
-    const unsigned long long e0 = (win_bits(w.M[0]) >> 52) - 52ull;             // biased exponent of u_0
+    const unsigned long long e0 = (win_bits(w.M0) >> 52) - 52ull;             // biased exponent of u_0
     for (int k = 0; k < W; ++k) out[k] = (double)d[k] * win_from_bits((e0 - (unsigned long long)(52 * k)) << 52);
     out[W] = (double)top * win_from_bits((e0 + 52ull) << 52);
     for (int k = 0; k < W; ++k) w.a[k] = 0ull;
@@ -314,10 +321,8 @@ EXB_HD bool winp_anchor_range(WindowP<W>& w, int emin, int emax) {
     const int b = lo + 52 * (W - 3) - 1;
     if (b < -984 + 52 * (W - 1) || b > kWinBMax) return false;
     const unsigned long long m0 = ((unsigned long long)(unsigned)(b + 52 + 1023) << 52) | 0x0008000000000000ull;
-    for (int k = 0; k < W; ++k) {
-        w.M[k] = win_from_bits(m0 - ((unsigned long long)(52 * k) << 52));
-        w.a[k] = 0ull;
-    }
+    w.M0 = win_from_bits(m0);
+    for (int k = 0; k < W; ++k) w.a[k] = 0ull;
     w.key0 = (unsigned)(lo + 1023) << 20;
     w.span = (unsigned)width << 20;
     w.cnt = 0u;
@@ -363,10 +368,8 @@ EXB_HD bool wins_anchor_range(WindowP<W>& w, int emin, int emax) {
     const int b = lo + 52 * (W - 2);
     if (b < -984 + 52 * (W - 1) || b > kWinBMax) return false;
     const unsigned long long m0 = ((unsigned long long)(unsigned)(b + 52 + 1023) << 52) | 0x0008000000000000ull;
-    for (int k = 0; k < W; ++k) {
-        w.M[k] = win_from_bits(m0 - ((unsigned long long)(52 * k) << 52));
-        w.a[k] = 0ull;
-    }
+    w.M0 = win_from_bits(m0);
+    for (int k = 0; k < W; ++k) w.a[k] = 0ull;
     w.key0 = (unsigned)(lo + 1023) << 20;
     w.span = (unsigned)width << 20;
     w.cnt = 0u;
@@ -380,9 +383,9 @@ EXB_HD void wins_add(WindowP<W>& w, double x) {
 #pragma unroll
 #endif
     for (int k = 0; k < W; ++k) {
-        const double t = EXB_ADD(r, w.M[k]);
+        const double t = EXB_ADD(r, winp_M(w, k));
         w.a[k] += win_bits(t);
-        if (k < W - 1) r = EXB_SUB(r, EXB_SUB(t, w.M[k]));
+        if (k < W - 1) r = EXB_SUB(r, EXB_SUB(t, winp_M(w, k)));
     }
 }
 
@@ -392,14 +395,14 @@ EXB_HD void wins_drain(WindowP<W>& w, double (&out)[W + 1]) {
     if (w.cnt == 0u) return;
     const unsigned long long c = w.cnt;
     long long d[W];
-    for (int k = 0; k < W; ++k) d[k] = (long long)(w.a[k] - c * win_bits(w.M[k]));
+    for (int k = 0; k < W; ++k) d[k] = (long long)(w.a[k] - c * win_bits(winp_M(w, k)));
     for (int k = W - 1; k > 0; --k) {
         d[k - 1] += d[k] >> kDigits;
         d[k] &= kLimbMask;
     }
     const long long top = d[0] >> kDigits;
     d[0] &= kLimbMask;
-    const unsigned long long e0 = (win_bits(w.M[0]) >> 52) - 52ull;
+    const unsigned long long e0 = (win_bits(w.M0) >> 52) - 52ull;
     for (int k = 0; k < W; ++k) out[k] = (double)d[k] * win_from_bits((e0 - (unsigned long long)(52 * k)) << 52);
     out[W] = (double)top * win_from_bits((e0 + 52ull) << 52);
     for (int k = 0; k < W; ++k) w.a[k] = 0ull;
