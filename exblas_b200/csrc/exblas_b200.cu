@@ -387,7 +387,6 @@ typedef void (*gemv_fn)(const GemvParams);
 // a deep window of 8-byte loads, the expansion), which a 512-thread CTA cannot have without spills.
 constexpr int kGemvT = 384;
 constexpr int gemv_groups_in_flight(int f) { return f <= 4 ? 4 : 3; }
-constexpr int kGemvWinU = 8;        // column groups in flight per thread in the register-window kernel
 
 template <int F, bool EE, bool A1>
 gemv_fn gemv_ptr() {

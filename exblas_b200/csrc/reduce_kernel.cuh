@@ -901,7 +901,7 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide(const double* pa, cons
             since_norm += W + 1;
         }
         since_norm += missed * (8 + W + 1);                     // ordinary deposits + a drain when the window moves
-        if (since_norm > kMaxDepositsPerNormalize - DW * (8 + W + 1) - 16) {
+        if (since_norm > kMaxDepositsPerNormalize - 2 * DW * (8 + W + 1) - (W + 1) - 16) {   // room for one more block of half rows + a flush
             bound_column(col, stride);
             since_norm = 0;
         }
@@ -1003,7 +1003,7 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, 
             since_norm += W + 1;
         }
         since_norm += missed * (4 + W + 1);
-        if (since_norm > kMaxDepositsPerNormalize - DW * (4 + W + 1) - 16) {
+        if (since_norm > kMaxDepositsPerNormalize - DW * (4 + W + 1) - (W + 1) - 16) {       // room for one more block + a flush
             bound_column(col, stride);
             since_norm = 0;
         }
