@@ -477,7 +477,8 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     }
     // superaccumulator-only mode, alpha == 1, unit row stride: the register-window kernel (window.cuh);
     // it stages its slice of x in shared memory, so a part holds at most kGemvXsMax columns
-    const bool windowed = f == 0 && alpha == 1.0 && rs == 1 && h->opt_window;
+    // (a part holds at most kGemvXsMax columns; beyond 1024 parts the per-part limbs could overflow when summed)
+    const bool windowed = f == 0 && alpha == 1.0 && rs == 1 && h->opt_window && (n + kGemvXsMax - 1) / kGemvXsMax <= 1024;
     // launch shapes of the window kernel (option "gemv_n_shape"): rows per CTA x column groups in flight
     struct NShape { int T; gemv_fn fn; };
     static const NShape nshapes[] = {
