@@ -752,7 +752,7 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "fused_allreduce")) {
         h->opt_fused = value != 0;
     } else if (!strcmp(name, "gemv_parts")) {
-        if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;
+        if (value < 0 || value > 1024) return EXBLAS_B200_EINVAL;   // per-part limbs are bounded by 2^52 + 2^11, not normalised: 1024 of them fit
         h->opt_gemv_parts = value;
     } else if (!strcmp(name, "gemv_t_shape")) {
         if (value < 0 || value > 3) return EXBLAS_B200_EINVAL;

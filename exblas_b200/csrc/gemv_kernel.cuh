@@ -615,7 +615,7 @@ __global__ void exgemv_finish_kernel(const GemvParams prm) {
     for (int j = 0; j < kLimbs; ++j) {
         long long s = 0;
         for (int p = 0; p < prm.parts; ++p) s += prm.scratch[((long long)p * kLimbs + j) * prm.m + row];
-        acc[j] = s;                                          // parts <= 2048 normalised limbs: no overflow
+        acc[j] = s;                                          // parts <= 1024 bounded limbs (< 2^52 + 2^11 each): no overflow
     }
     unsigned st = 0;
     for (int p = 0; p < prm.parts; ++p) st |= prm.row_status[(long long)p * prm.m + row];
