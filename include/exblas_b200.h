@@ -67,9 +67,12 @@ int exblas_b200_destroy(exblas_b200_handle_t handle);
 int exblas_b200_set_stream(exblas_b200_handle_t handle, void* stream);
 
 /* Tuning knobs (performance only, never the result): "block_threads" (multiple of 32, <= 512),
- * "blocks" (0 = one per SM), "host_chunk_elems", "gemv_parts" (0 = automatic column split), "adaptive" (1 = a warp bypasses the expansion and
- * deposits straight into its superaccumulators while the expansion overflows on most elements;
- * 0 = always walk all fpe levels, as the reference kernels do). */
+ * "blocks" (0 = one per SM), "host_chunk_elems", "gemv_parts" (0 = automatic column split, <= 1024),
+ * "adaptive" (1 = a warp bypasses the expansion and deposits straight into its superaccumulators while
+ * the expansion overflows on most elements; 0 = always walk all fpe levels, as the reference kernels do),
+ * "window" (register window of the superaccumulator-only kernels: 0 off, 1 narrow windows, 2 narrow then
+ * wide windows (default), 3 wide only), "gemv_n_shape" (0..2) / "gemv_t_shape" (0..3): launch shapes of
+ * the ExGEMV window kernels, "fused_allreduce" (1 = exchange limbs inside the kernel once peers are attached). */
 int exblas_b200_set_option(exblas_b200_handle_t handle, const char* name, int64_t value);
 
 /* ---- synchronous entry points: the ones a reference binding calls --------------------------- */
