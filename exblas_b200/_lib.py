@@ -12,7 +12,7 @@ LIMBS = 39
 ROUND_REFERENCE = 0
 ROUND_EXACT = 1
 
-ST_NAN, ST_POSINF, ST_NEGINF, ST_TOOLARGE, ST_TOOSMALL = 1, 2, 4, 8, 16
+ST_NAN, ST_POSINF, ST_NEGINF, ST_TOOLARGE, ST_TOOSMALL, ST_PEERTIMEOUT = 1, 2, 4, 8, 16, 32
 
 _dp = C.c_void_p           # data pointers are passed as raw addresses (host or device)
 _i64 = C.c_int64
@@ -54,6 +54,9 @@ SIGNATURES = {
     "exblas_b200_last_status": (C.c_int, [_h, C.POINTER(C.c_uint32)]),
     "exblas_b200_last_error": (C.c_char_p, [_h]),
     "exblas_b200_launch_count": (_i64, [_h]),
+    "exblas_b200_phase_times": (_i64, [_h, C.POINTER(C.c_uint64), _i64]),
+    "exblas_b200_microbench": (C.c_int, [_h, C.c_int, _dp, _i64, C.POINTER(C.c_double)]),
+    "exblas_b200_last_kernel": (C.c_char_p, [_h]),
 }
 
 _lib = None

@@ -205,6 +205,24 @@ class Handle:
     def launch_count(self) -> int:
         return int(self.lib.exblas_b200_launch_count(self._h))
 
+    def last_kernel(self) -> str:
+        return self.lib.exblas_b200_last_kernel(self._h).decode()
+
+    def microbench(self, what: int, d_buf=None) -> float:
+        """0: FP64 DADD lane-instructions/s; 1: read-only stream GB/s over the device tensor d_buf."""
+        res = C.c_double()
+        addr, n = (0, 0)
+        if d_buf is not None:
+            addr, n, _ = _address(d_buf)
+        check(self.lib.exblas_b200_microbench(self._h, what, addr, n, C.byref(res)), self._h)
+        return res.value
+
+    def phase_times(self) -> np.ndarray:
+        """With option "phase_timing" = 1: [CTAs][16] globaltimer stamps (ns) of the last reduction kernel."""
+        buf = (C.c_uint64 * (2048 * 16))()
+        nb = int(self.lib.exblas_b200_phase_times(self._h, buf, 2048 * 16))
+        return np.frombuffer(buf, dtype=np.uint64)[:nb * 16].reshape(nb, 16).copy()
+
 
 def _check_extent(n, inc, off, size, name):
     if n < 0 or inc < 1 or off < 0:

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libexblas_b200.so")
 SOURCES = [os.path.join(CSRC, "exblas_b200.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("reduce_kernel.cuh", "superacc.cuh", "window.cuh", "gemv_kernel.cuh",
-                                                   "segments_kernel.cuh")] + [os.path.join(HERE, "..", "include", "exblas_b200.h")]
+                                                   "segments_kernel.cuh", "microbench.cuh")] + [os.path.join(HERE, "..", "include", "exblas_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

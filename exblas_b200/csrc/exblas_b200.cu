@@ -24,6 +24,7 @@
 #include "reduce_kernel.cuh"
 #include "gemv_kernel.cuh"
 #include "segments_kernel.cuh"
+#include "microbench.cuh"
 
 using namespace exb;
 
@@ -111,6 +112,13 @@ struct exblas_b200_handle_s {
     int64_t opt_gemv_t_shape = 2;
     int64_t opt_gemv_n_shape = 1;
     int64_t opt_window = 2;                 // register window in the superaccumulator-only kernels (performance only)
+    bool opt_shape_fixed = false;           // "block_threads" / "blocks" were set by hand: no size-dependent launch shape
+    int64_t opt_solo_max = (int64_t)1 << 13;    // vectors up to this length: one CTA, published from shared memory
+    int64_t opt_small_max = (int64_t)1 << 22;   // vectors up to this length: 256-thread CTAs
+    int64_t opt_world_size = 0;             // declared number of ranks of a multi-GPU job (0 = not declared)
+    int64_t opt_peer_timeout_ms = 600000;   // fused exchange: how long the closing warp waits for a peer (0 = for ever)
+    unsigned long long* d_phase = nullptr;  // diagnostics: per-CTA phase stamps of the last reduction kernel
+    int phase_blocks = 0;
     void* comm = nullptr;
     int nranks = 1;
     // fused peer-memory exchange (exblas_b200_peer_export / peer_attach)
@@ -122,6 +130,7 @@ struct exblas_b200_handle_s {
     int64_t launches = 0;
     bool acc_pending = false;               // workspace accumulator holds an unfinished (chunked) reduction
     uint32_t last_status = 0;
+    std::string last_kernel;                // name of the reduction kernel launched last (bench.py reports it)
     std::string err;
 };
 
@@ -218,38 +227,51 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     }
     h->acc_pending = finalize ? false : true;      // an open (chunked) reduction leaves its partial sum in gacc
 
-    int T = (int)h->opt_block_threads;
-    int64_t max_blocks = h->opt_blocks > 0 ? h->opt_blocks : h->num_sms;
-    if (h->opt_blocks == 0) {
-        // latency regime: one CTA publishes straight from shared memory (no global merge round trip)
-        if (n <= (1 << 13)) { T = 128; max_blocks = 1; }
-        else if (n <= (1 << 15)) { max_blocks = 1; }
-        else if (n <= (1 << 18)) { T = 128; }          // small CTAs, little shared memory to clear
-    }
-    // superaccumulator-only kernels (exblas_reduce0_kernel) tile by rows of T * 4 elements
-    const int U = f == 0 ? 1 : vectors_in_flight(f, ee, dot);     // exblas_reduce0_kernel tiles by rows of T * 4 elements
-    const int64_t tile = (int64_t)T * 4 * U;
-
-    // vector body needs unit strides and, for ExDOT, the same 32-byte phase on both streams
+    // vector region: unit strides and, for ExDOT, the same 32-byte phase on both streams
     p.head = 0;
-    p.ntiles = 0;
+    p.nvec = 0;
     if (inca == 1 && (!dot || incb == 1) && ((uintptr_t)a % 8 == 0) && (!dot || (uintptr_t)b % 8 == 0)) {
         const int64_t mis_a = (int64_t)(((uintptr_t)a % 32) / 8);
         const int64_t head = (4 - mis_a) % 4;
         bool ok = true;
         if (dot) ok = ((uintptr_t)b % 32) / 8 == (uintptr_t)mis_a;
-        if (ok && n > head) {
+        if (ok && n >= head + 4) {
             p.head = head;
-            p.ntiles = (n - head) / tile;
-            if (p.ntiles == 0) p.head = 0;
+            p.nvec = (n - head) / 4;
         }
     }
-    int64_t blocks = max_blocks;
-    int64_t want;
-    if (p.ntiles > 0) want = p.ntiles;
-    else want = (n + T - 1) / T;
-    if (want < 1) want = 1;
-    if (blocks > want) blocks = want;
+    // launch shape.  Large vectors: one 512-thread CTA per SM.  Below that the fixed costs of a launch (clearing and
+    // merging T columns per CTA, the global merge round trip) dominate, so the CTAs shrink with n, and the
+    // smallest vectors take ONE CTA that publishes straight from shared memory (no global round trip at all).
+    int T = (int)h->opt_block_threads;
+    int64_t max_blocks = h->opt_blocks > 0 ? h->opt_blocks : h->num_sms;
+    const int64_t work = p.nvec > 0 ? p.nvec : (n + 7) / 8;      // 256-bit vectors (scalar path: groups of 8 loads)
+    p.peer_timeout_ns = (unsigned long long)h->opt_peer_timeout_ms * 1000000ull;
+    p.phase = h->d_phase;
+    if (!h->opt_shape_fixed && n <= h->opt_solo_max && p.fresh && finalize) {
+        // latency regime: the small single-CTA kernel (every fpe value: fpe never changes the result)
+        const int64_t per_thread4 = p.nvec > 0 ? (p.nvec + 3) / 4 : (n + 3) / 4;
+        T = per_thread4 <= 128 ? 128 : (per_thread4 <= 256 ? 256 : 512);
+        if (p.nvec > 4 * (int64_t)T) p.nvec = 4 * (int64_t)T;    // (only if solo_max_elems was raised beyond 2^13: rest is scalar)
+        p.iters = 0;
+        if (h->d_phase) h->phase_blocks = 1;
+        kernel_fn sfn = dot ? exblas_small_kernel<true> : exblas_small_kernel<false>;
+        CK(allow_big_smem((const void*)sfn, h->device));
+        void* sargs[] = {(void*)&p};
+        CK(cudaLaunchKernel((const void*)sfn, dim3(1), dim3((unsigned)T), sargs, (size_t)T * kLimbs * sizeof(long long), h->stream));
+        h->launches += 1;
+        h->last_kernel = std::string(dot ? "exblas_small_kernel<DOT=1>" : "exblas_small_kernel<DOT=0>") + " grid=1 block=" + std::to_string(T);
+        return EXBLAS_B200_OK;
+    }
+    if (!h->opt_shape_fixed && n <= h->opt_small_max) T = 256;
+    int64_t blocks = (work + 4 * (int64_t)T - 1) / (4 * (int64_t)T);   // four vectors per thread keep the loads overlapped
+    if (blocks < 1) blocks = 1;
+    if (blocks > max_blocks) blocks = max_blocks;
+    // unrolled vector body: the same number of tiles in every CTA; the rest is spread over all threads (reduce_finish)
+    const int U = f == 0 ? 1 : vectors_in_flight(f, ee, dot);     // exblas_reduce0_kernel tiles by rows of T * 4 elements
+    p.iters = p.nvec / ((int64_t)T * U * blocks);
+    if (p.iters > 0x7fffffff) p.iters = 0x7fffffff;               // (2^31 tiles per CTA: beyond any memory)
+    if (h->d_phase) h->phase_blocks = (int)blocks;
 
     // superaccumulator-only mode: window loop with 6 (ExSUM) / 2 (ExDOT) rows in flight, direct loop with 8 / 4
     // (measured at n = 2^30 against 4/8, 8/8 and 3/4, 4/4: profiles/f0_window_r01.jsonl)
@@ -260,6 +282,16 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     void* args[] = {(void*)&p};
     CK(cudaLaunchKernel((const void*)fn, dim3((unsigned)blocks), dim3((unsigned)T), args, smem, h->stream));
     h->launches += 1;
+    {
+        char nm[160];
+        if (f == 0)
+            snprintf(nm, sizeof nm, "exblas_reduce0_kernel<DOT=%d,DW=%d,DD=%d,MAXT=%d> grid=%lld block=%d", dot ? 1 : 0,
+                     dot ? 2 : 6, dot ? 4 : 8, kMaxT, (long long)blocks, T);
+        else
+            snprintf(nm, sizeof nm, "exblas_reduce_kernel<F=%d,EE=%d,DOT=%d,U=%d,MAXT=%d> grid=%lld block=%d", f, ee ? 1 : 0,
+                     dot ? 1 : 0, U, kMaxT, (long long)blocks, T);
+        h->last_kernel = nm;
+    }
     return EXBLAS_B200_OK;
 }
 
@@ -378,6 +410,12 @@ int fetch_result(exblas_b200_handle_t h, double* result, int64_t* limbs, uint32_
     if (status) *status = h->h_res->status;
     if (limbs)
         for (int j = 0; j < kLimbs; ++j) limbs[j] = h->h_res->limbs[j];
+    if (h->h_res->status & kStPeerTimeout) {
+        // the ranks no longer agree on what has been summed: this is an error, not a data property
+        h->err = "fused multi-GPU exchange: a peer's limbs did not arrive within peer_timeout_ms; the value (NaN) and limbs are "
+                 "partial, and the peers must be re-attached (exblas_b200_peer_export / peer_attach) before the next reduction";
+        return EXBLAS_B200_EPEER;
+    }
     return EXBLAS_B200_OK;
 }
 
@@ -478,7 +516,10 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     // superaccumulator-only mode, alpha == 1, unit row stride: the register-window kernel (window.cuh);
     // it stages its slice of x in shared memory, so a part holds at most kGemvXsMax columns
     // (a part holds at most kGemvXsMax columns; beyond 1024 parts the per-part limbs could overflow when summed)
-    const bool windowed = f == 0 && alpha == 1.0 && rs == 1 && h->opt_window && (n + kGemvXsMax - 1) / kGemvXsMax <= 1024;
+    // Like 'T' above, every fpe value takes it: fpe only selects HOW the exact sum is accumulated, never the result, and
+    // the window kernel streams at 2.8x the rate of the expansion kernels (round 1: 5.6 against 2.0 TB/s at 32768^2).
+    // Option "window" = 0 keeps the expansion kernels (exgemv_n_kernel<F, EE, ...>) reachable.
+    const bool windowed = alpha == 1.0 && rs == 1 && h->opt_window && (n + kGemvXsMax - 1) / kGemvXsMax <= 1024;
     // launch shapes of the window kernel (option "gemv_n_shape"): rows per CTA x column groups in flight
     struct NShape { int T; gemv_fn fn; };
     static const NShape nshapes[] = {
@@ -664,6 +705,7 @@ const char* exblas_b200_strerror(int code) {
         case EXBLAS_B200_ENOGPU: return "no usable CUDA device";
         case EXBLAS_B200_ENCCL: return "NCCL error";
         case EXBLAS_B200_ENOMEM: return "out of memory";
+        case EXBLAS_B200_EPEER: return "multi-GPU peer exchange timed out";
         default: return "unknown error";
     }
 }
@@ -723,6 +765,7 @@ int exblas_b200_destroy(exblas_b200_handle_t h) {
         if (h->peer_box[r] && h->peer_box[r] != h->d_mailbox) cudaIpcCloseMemHandle(h->peer_box[r]);
     if (h->d_mailbox) cudaFree(h->d_mailbox);
     if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
+    if (h->d_phase) cudaFree(h->d_phase);
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_res) cudaFree(h->d_res);
     if (h->h_res) cudaFreeHost(h->h_res);
@@ -746,9 +789,38 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     if (!strcmp(name, "block_threads")) {
         if (value < 32 || value > kMaxT || value % 32) return EXBLAS_B200_EINVAL;
         h->opt_block_threads = value;
+        h->opt_shape_fixed = true;
     } else if (!strcmp(name, "blocks")) {
-        if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;    // 2048 partials of < 2^52 fit a limb
+        if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;    // 2048 partials of < 2^52 + 2^10 fit a limb
         h->opt_blocks = value;
+        h->opt_shape_fixed = true;
+    } else if (!strcmp(name, "auto_shape")) {                        // back to the size-dependent launch shape
+        h->opt_shape_fixed = value == 0;
+        if (value) {
+            h->opt_blocks = 0;
+            h->opt_block_threads = kMaxT;
+        }
+    } else if (!strcmp(name, "solo_max_elems")) {
+        if (value < 0) return EXBLAS_B200_EINVAL;
+        h->opt_solo_max = value;
+    } else if (!strcmp(name, "small_max_elems")) {
+        if (value < 0) return EXBLAS_B200_EINVAL;
+        h->opt_small_max = value;
+    } else if (!strcmp(name, "world_size")) {
+        if (value < 0) return EXBLAS_B200_EINVAL;
+        h->opt_world_size = value;
+    } else if (!strcmp(name, "peer_timeout_ms")) {
+        if (value < 0) return EXBLAS_B200_EINVAL;
+        h->opt_peer_timeout_ms = value;
+    } else if (!strcmp(name, "phase_timing")) {                      // diagnostics: globaltimer stamps per CTA and phase
+        if (value && !h->d_phase) {
+            if (cudaSetDevice(h->device) != cudaSuccess) return EXBLAS_B200_ECUDA;
+            if (cudaMalloc(&h->d_phase, (size_t)2048 * kPhaseSlots * sizeof(unsigned long long)) != cudaSuccess) return EXBLAS_B200_ECUDA;
+            cudaMemset(h->d_phase, 0, (size_t)2048 * kPhaseSlots * sizeof(unsigned long long));
+        } else if (!value && h->d_phase) {
+            cudaFree(h->d_phase);
+            h->d_phase = nullptr;
+        }
     } else if (!strcmp(name, "fused_allreduce")) {
         h->opt_fused = value != 0;
     } else if (!strcmp(name, "gemv_parts")) {
@@ -1013,6 +1085,12 @@ int exblas_b200_allreduce_async(exblas_b200_handle_t h, int round_mode) {
     CK(cudaSetDevice(h->device));
     // with the fused exchange active the closing kernel has already merged and rounded
     if (h->peer_ranks > 1 && h->opt_fused) return EXBLAS_B200_OK;
+    if (h->opt_world_size > 1 && h->nranks != h->opt_world_size) {
+        // the caller declared a multi-rank job (option "world_size") but no transport joins that many ranks:
+        // finishing locally would silently return this rank's shard only
+        h->err = "allreduce: world_size > 1 but neither exblas_b200_comm_init nor an attached fused peer exchange covers it";
+        return EXBLAS_B200_ENCCL;
+    }
     if (h->nranks > 1) {
         if (!h->comm) {
             h->err = "exblas_b200_comm_init was not called";
@@ -1041,7 +1119,62 @@ int exblas_b200_last_status(exblas_b200_handle_t h, uint32_t* status_flags) {
 
 const char* exblas_b200_last_error(exblas_b200_handle_t h) { return h ? h->err.c_str() : "null handle"; }
 
+int64_t exblas_b200_phase_times(exblas_b200_handle_t h, uint64_t* out, int64_t capacity) {
+    if (!h || !h->d_phase || !out) return 0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return 0;
+    cudaStreamSynchronize(h->stream);
+    int64_t words = (int64_t)h->phase_blocks * kPhaseSlots;
+    if (words > capacity) words = capacity / kPhaseSlots * kPhaseSlots;
+    if (words <= 0) return 0;
+    if (cudaMemcpy(out, h->d_phase, (size_t)words * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    cudaMemset(h->d_phase, 0, (size_t)2048 * kPhaseSlots * sizeof(unsigned long long));
+    return words / kPhaseSlots;
+}
+
 int64_t exblas_b200_launch_count(exblas_b200_handle_t h) { return h ? h->launches : 0; }
+
+const char* exblas_b200_last_kernel(exblas_b200_handle_t h) { return h ? h->last_kernel.c_str() : ""; }
+
+int exblas_b200_microbench(exblas_b200_handle_t h, int what, const double* d_buf, int64_t n, double* result) {
+    if (!h || !result) return EXBLAS_B200_EINVAL;
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float ms = 0.f;
+    int rc = [&]() -> int {
+        if (what == 0) {                    // FP64 pipe: DADD lane-instructions per second
+            const int iters = 20000;
+            mb_dadd_kernel<<<h->num_sms, 1024, 0, h->stream>>>((double*)h->d_res, 100, 1.0);
+            CK(cudaEventRecord(e0, h->stream));
+            mb_dadd_kernel<<<h->num_sms, 1024, 0, h->stream>>>((double*)h->d_res, iters, 1.0);
+            CK(cudaEventRecord(e1, h->stream));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            *result = (double)h->num_sms * 1024.0 * 8.0 * iters / (ms * 1e-3);
+            h->launches += 2;
+            return EXBLAS_B200_OK;
+        }
+        if (what == 1) {                    // read-only stream over d_buf[0, n): GB/s
+            if (!d_buf || n < 4 || ((uintptr_t)d_buf % 32) != 0 || !is_device_pointer(d_buf)) return EXBLAS_B200_EINVAL;
+            const long long nvec = n / 4;
+            const int blocks = h->num_sms * 4, reps = 3;
+            mb_read_kernel<<<blocks, 512, 0, h->stream>>>(d_buf, nvec, (double*)h->d_res);
+            CK(cudaEventRecord(e0, h->stream));
+            for (int r = 0; r < reps; ++r) mb_read_kernel<<<blocks, 512, 0, h->stream>>>(d_buf, nvec, (double*)h->d_res);
+            CK(cudaEventRecord(e1, h->stream));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            *result = (double)reps * (double)nvec * 32.0 / (ms * 1e-3) / 1e9;
+            h->launches += 1 + reps;
+            return EXBLAS_B200_OK;
+        }
+        return EXBLAS_B200_EINVAL;
+    }();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
 
 }  // extern "C"
 

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
 #pragma unroll
         for (int i = 0; i < F; ++i)
 #pragma unroll
-            for (int m = 0; m < kM; ++m) deposit(col, stride, a[i][m], status);
+            for (int m = 0; m < kM; ++m) deposit_sum(col, stride, a[i][m], status);
     }
     bound_column(col, stride);
     if (status && valid) atomicOr(&prm.ws->status, status);

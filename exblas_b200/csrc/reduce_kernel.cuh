@@ -45,30 +45,36 @@ struct Result {                          // published by the last CTA
     long long flagcnt[kFlagSlots];       // flagcnt[k] = 1 when status bit k is set (contiguous with limbs)
 };
 
-// Peer-memory mailbox for the fused limb exchange over NVLink / NVSwitch.  Rank r's last CTA stores
-// its 44 int64 (normalised limbs + status-flag counters) into slot [epoch & 1][r] of EVERY rank's
-// mailbox with plain peer stores, then publishes the epoch with a release store; each rank then
-// waits for all its slots of this epoch, sums them as integers, normalises and rounds -- inside the
-// reduction kernel, with no NCCL call and no extra launch.  Two slot sets suffice: a rank cannot
-// start epoch e+2 before every peer has finished reading epoch e (it needs their epoch e+1 data).
+// Peer-memory mailbox for the fused limb exchange over NVLink / NVSwitch.  Rank r's closing warp stores its
+// message into slot [epoch & 1][r] of EVERY rank's mailbox with plain 8-byte peer stores; every word carries its
+// own 12-bit sequence tag next to a 52-bit payload (the "LL" idea: data and flag travel in ONE store, so there
+// is no fence, no separate flag store and no second NVLink traversal).  Each rank polls the words of all its
+// slots until they carry this epoch's tag, sums them as integers, normalises and rounds -- inside the reduction
+// kernel, with no NCCL call and no extra launch.  Two slot sets suffice: a rank cannot start epoch e+2 before
+// every peer has finished reading epoch e (it needs their epoch e+1 data first).
+//   word w < 38 : limb w (normalised: in [0, 2^52))
+//   word 38, 39 : limb 38 (signed, 64 bits) as low 52 bits / arithmetic high 12 bits
+//   word 40     : status flags
 constexpr int kMaxPeers = 8;
-constexpr int kMsgWords = kLimbs + kFlagSlots;   // 44
+constexpr int kMsgWords = kLimbs + 2;            // 41
 struct MailSlot {
-    unsigned long long data[kMsgWords];
-    unsigned long long seq;
-    unsigned long long pad[3];                   // 48 words = 384 B per slot
+    unsigned long long data[48];                 // 41 used; 384 B per slot
 };
 struct Mailbox {
     MailSlot slot[2][kMaxPeers];
 };
+EXB_HD unsigned long long peer_tag(unsigned long long epoch) { return (epoch % 4095ull) + 1ull; }   // never 0 (= empty mailbox)
+
+constexpr int kPhaseSlots = 16;          // per-CTA globaltimer stamps (diagnostics: option "phase_timing")
 
 struct ReduceParams {
     const double* a;                     // already offset by `offset`
     const double* b;                     // ExDOT only
     long long n;                         // number of elements
     long long inca, incb;                // element strides
-    long long head;                      // scalar elements before the vector body
-    long long ntiles;                    // full tiles in the vector body (0 => all scalar)
+    long long head;                      // scalar elements before the 32-byte aligned vector region (0 when nvec == 0)
+    long long nvec;                      // full 256-bit vectors after the head (0 => everything is scalar)
+    long long iters;                     // tiles (of T * U vectors) every CTA streams in the unrolled vector body
     Workspace* ws;
     Result* out;
     int finalize;                        // 1: publish value/limbs/status and reset workspace
@@ -81,6 +87,8 @@ struct ReduceParams {
     Mailbox* peers[kMaxPeers];
     int nranks, rank;
     unsigned long long epoch;            // identifies this collective reduction (same on every rank, >= 1)
+    unsigned long long peer_timeout_ns;  // give up waiting for a peer after this long (0 = wait for ever)
+    unsigned long long* phase;           // optional [gridDim.x][kPhaseSlots] globaltimer stamps (nullptr = off)
 };
 
 EXB_D Vec4 ldg256(const double* p) {
@@ -113,6 +121,16 @@ EXB_D unsigned long long ld_relaxed_sys(const unsigned long long* p) {
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+
+EXB_D unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define EXB_PHASE(k)                                                                                         \
+    do {                                                                                                     \
+        if (prm.phase != nullptr && threadIdx.x == 0) prm.phase[(size_t)blockIdx.x * kPhaseSlots + (k)] = globaltimer_ns(); \
+    } while (0)
 
 EXB_D bool nonzero_bits(double x) {
     return (((unsigned)__double2hiint(x) & 0x7fffffffu) | (unsigned)__double2loint(x)) != 0u;
@@ -333,32 +351,158 @@ EXB_D void mul_add1(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][ex
     if (nonzero_bits(r)) deposit(col, stride, r, status);
 }
 
-// Carry-normalise a 39-limb array that lives in shared memory: pull it into registers first so the
-// carry chain runs at ALU latency instead of shared-memory round trips.
-EXB_D bool normalize_shared(long long* limbs) {
-    long long r[kLimbs];
-#pragma unroll
-    for (int j = 0; j < kLimbs; ++j) r[j] = limbs[j];
-    long long carry = 0;
-#pragma unroll
-    for (int j = 0; j < kLimbs - 1; ++j) {
-        const long long v = r[j] + carry;
-        carry = v >> kDigits;
-        r[j] = v & kLimbMask;
+// ------------------------------------------------------------------------------------------------
+// Warp-parallel limb arithmetic for the epilogue.  A 39-limb array is spread over one warp: lane l holds limb l
+// in `.a` (l = 0..31) and limb 32 + l in `.b` (l = 0..6; `.b` is zero in the other lanes).  Normalisation and
+// both roundings then cost a few dozen instructions and a handful of shuffles / votes instead of a 39-step
+// serial carry chain and serial limb scans by one thread (those were ~1.5 us of every launch).
+// ------------------------------------------------------------------------------------------------
+struct WarpLimbs { long long a, b; };
+constexpr unsigned kFullWarp = 0xffffffffu;
+
+EXB_D unsigned long long wl_ballot(bool pa, bool pb) {          // bit j = predicate of limb j
+    return (unsigned long long)__ballot_sync(kFullWarp, pa) | ((unsigned long long)(__ballot_sync(kFullWarp, pb) & 0x7fu) << 32);
+}
+EXB_D long long wl_get(const WarpLimbs& x, int k) {             // limb k (k warp-uniform, 0..38)
+    const long long va = __shfl_sync(kFullWarp, x.a, k & 31);
+    const long long vb = __shfl_sync(kFullWarp, x.b, k & 31);
+    return k < 32 ? va : vb;
+}
+EXB_D WarpLimbs wl_shift_up(const WarpLimbs& c, unsigned lane) {    // out.limb[j] = c.limb[j-1], out.limb[0] = 0
+    long long ua = __shfl_up_sync(kFullWarp, c.a, 1);
+    long long ub = __shfl_up_sync(kFullWarp, c.b, 1);
+    const long long a31 = __shfl_sync(kFullWarp, c.a, 31);
+    if (lane == 0) {
+        ua = 0;
+        ub = a31;
     }
-    r[kLimbs - 1] += carry;
-#pragma unroll
-    for (int j = 0; j < kLimbs; ++j) limbs[j] = r[j];
-    return r[kLimbs - 1] < 0;
+    WarpLimbs r;
+    r.a = ua;
+    r.b = ub;
+    return r;
+}
+EXB_D unsigned long long low_bits(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull)); }   // bits 0..n-1
+
+// Normal form (limbs 0..37 in [0, 2^52), limb 38 keeps the signed remainder: normalize(), superacc.cuh) of ANY
+// int64 limbs.  Two local splits bring every carry down to one bit, then the ripple is resolved with the
+// classic generate / propagate trick on vote masks: carries = ((g | p) + g) ^ p.  To keep every carry
+// non-negative, limbs 1..37 first borrow one unit of the limb above (+2^52 here, -1 there: value unchanged).
+// Returns true when the value is negative.
+EXB_D bool warp_normalize(WarpLimbs& x, unsigned lane) {
+    const bool has_b = lane < 7u, low_b = lane < 6u;             // .b: limbs 32..38; limb 38 (lane 6) is never reduced
+    const long long R = 1ll << kDigits;
+    WarpLimbs c, u;
+    // split 1: carries in [-2^11, 2^11)
+    c.a = x.a >> kDigits;
+    x.a &= kLimbMask;
+    c.b = low_b ? (x.b >> kDigits) : 0;
+    if (low_b) x.b &= kLimbMask;
+    u = wl_shift_up(c, lane);
+    x.a += u.a;
+    if (has_b) x.b += u.b;
+    // pre-borrow: limbs 1..37 += 2^52, limbs 2..38 -= 1
+    if (lane >= 1u) x.a += R;
+    if (lane >= 2u) x.a -= 1;
+    if (low_b) x.b += R;
+    if (has_b) x.b -= 1;
+    // split 2: limbs 0..37 are non-negative and below 2^54 now; carries in {0..3}
+    c.a = x.a >> kDigits;
+    x.a &= kLimbMask;
+    c.b = low_b ? (x.b >> kDigits) : 0;
+    if (low_b) x.b &= kLimbMask;
+    u = wl_shift_up(c, lane);
+    x.a += u.a;
+    if (has_b) x.b += u.b;
+    // limbs 0..37 in [0, 2^52 + 3]: one-bit carries, resolved by an integer add of the vote masks
+    const unsigned long long g = wl_ballot(x.a >= R, low_b && x.b >= R);
+    const unsigned long long pm = wl_ballot(x.a == R - 1, low_b && x.b == R - 1);
+    const unsigned long long carry = ((g | pm) + g) ^ pm;          // bit j = carry INTO limb j
+    x.a = (x.a + (long long)((carry >> lane) & 1ull)) & kLimbMask;
+    if (has_b) {
+        x.b += (long long)((carry >> (32u + lane)) & 1ull);
+        if (low_b) x.b &= kLimbMask;
+    }
+    return __shfl_sync(kFullWarp, x.b, 6) < 0;
 }
 
-// Sum one limb row over all T columns; result valid in lane 0.
-EXB_D long long row_sum(unsigned row_addr, unsigned T, unsigned lane) {
-    long long s = 0;
-    for (unsigned t = lane; t < T; t += 32) s += (long long)lds64(row_addr + 8u * t);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    return s;
+// Superaccumulator::Round() (superaccumulator.cpp:80-134) on normalised limbs held by the warp: the scans of
+// round_ref_compat() as votes, then the shared arithmetic (round_ref_parts).  Every lane returns the value.
+EXB_D double warp_round_ref(const WarpLimbs& x, bool negative) {
+    const unsigned long long nz = wl_ballot(x.a != 0, x.b != 0);
+    int i = nz ? 63 - __clzll((long long)nz) : -1;                                       // :91-94
+    if (negative && i >= 0) {                                                            // :95-101
+        const unsigned long long ones = wl_ballot((x.a & kLimbMask) == kLimbMask, (x.b & kLimbMask) == kLimbMask);
+        const unsigned long long cand = ~ones & low_bits(i + 1);
+        i = cand ? 63 - __clzll((long long)cand) : -1;
+    }
+    const long long acc_i = wl_get(x, i < 0 ? 0 : i);
+    const long long acc_im1 = wl_get(x, i < 1 ? 0 : i - 1);
+    // :116-119 -- limbs 0 .. i-2; for a negative value every term (2^52 - acc[j]) is non-zero
+    const bool sticky = i >= 2 && (negative || (nz & low_bits(i - 1)) != 0ull);
+    return round_ref_parts(i, acc_i, acc_im1, sticky, negative);
+}
+
+// Correct rounding (round_exact(), superacc.cuh) on normalised limbs held by the warp.
+__device__ __noinline__ double warp_round_exact(const WarpLimbs& x, bool negative, unsigned lane) {
+    unsigned long long ma = (unsigned long long)x.a, mb = (unsigned long long)x.b;
+    if (negative) {      // magnitude = two's complement negation, digit by digit: the +1 ripples through the zero limbs
+        const unsigned long long nz = wl_ballot(x.a != 0, x.b != 0);
+        const int tz = __ffsll((long long)nz) - 1;               // lowest non-zero limb (the value is not zero)
+        const long long R = 1ll << kDigits;
+        const int ja = (int)lane, jb = 32 + (int)lane;
+        ma = ja < tz ? 0ull : (unsigned long long)((ja == tz ? R : R - 1) - x.a);
+        if (lane < 6u) mb = jb < tz ? 0ull : (unsigned long long)((jb == tz ? R : R - 1) - x.b);
+        else if (lane == 6u) mb = (unsigned long long)((tz == 38 ? 0ll : -1ll) - x.b);
+        else mb = 0ull;
+    }
+    const unsigned long long mz = wl_ballot(ma != 0ull, mb != 0ull);
+    const int top = mz ? 63 - __clzll((long long)mz) : -1;
+    WarpLimbs m;
+    m.a = (long long)ma;
+    m.b = (long long)mb;
+    const unsigned long long m_top = (unsigned long long)wl_get(m, top < 0 ? 0 : top);
+    const unsigned long long m1 = top >= 1 ? (unsigned long long)wl_get(m, top - 1) : 0ull;
+    const unsigned long long m2 = top >= 2 ? (unsigned long long)wl_get(m, top - 2) : 0ull;
+    const bool sticky = top >= 3 && (mz & low_bits(top - 2)) != 0ull;       // limbs 0 .. top-3
+    return round_exact_parts(top, m_top, m1, m2, sticky, negative);
+}
+
+// value from limbs + status flags (finalize_value(), superacc.cuh); x must be normalised
+EXB_D double warp_value(const WarpLimbs& x, bool negative, unsigned st, int round_mode, unsigned lane) {
+    if ((st & kStNaN) || ((st & kStPosInf) && (st & kStNegInf)) || (st & kStPeerTimeout)) return __longlong_as_double(0x7ff8000000000000ll);
+    if (st & kStPosInf) return __longlong_as_double(0x7ff0000000000000ll);
+    if (st & kStNegInf) return __longlong_as_double(0xfff0000000000000ll);
+    return round_mode ? warp_round_exact(x, negative, lane) : warp_round_ref(x, negative);
+}
+
+// Sum one limb row over all T columns WITHOUT requiring the columns to be bounded first: the low 52 bits and the
+// carry-save bits of every limb are summed separately (the carry part belongs to the row above), so any int64
+// limb is fine and the separate bound_column pass before the merge is gone.  The cross-lane step is four
+// independent 32-bit REDUX (three 19-bit chunks of the low part + the carry part) instead of a 15-deep chain of
+// dependent shuffles, which used to dominate the epilogue (2-3 us of every launch).  Results valid in all lanes.
+EXB_D void row_sum_split(unsigned row_addr, unsigned T, unsigned lane, long long& lo, int& hi) {
+    unsigned long long slo = 0;
+    int shi = 0;
+#pragma unroll 4
+    for (unsigned t = lane; t < T; t += 32) {
+        const long long v = (long long)lds64(row_addr + 8u * t);
+        slo += (unsigned long long)(v & kLimbMask);
+        shi += (int)(v >> kDigits);
+    }
+    // slo < (T / 32) * 2^52 <= 2^57: chunks of 19 bits, each lane sum < 2^24
+    const unsigned r0 = __reduce_add_sync(kFullWarp, (unsigned)slo & 0x7ffffu);
+    const unsigned r1 = __reduce_add_sync(kFullWarp, (unsigned)(slo >> 19) & 0x7ffffu);
+    const unsigned r2 = __reduce_add_sync(kFullWarp, (unsigned)(slo >> 38));
+    hi = __reduce_add_sync(kFullWarp, shi);                    // |.| <= 1024 * 2^11
+    lo = (long long)((unsigned long long)r0 + ((unsigned long long)r1 << 19) + ((unsigned long long)r2 << 38));   // < 1024 * 2^52
+}
+
+// ticket counter with acquire + release semantics at GPU scope: orders this warp's REDs (made visible to lane 0 by
+// __syncwarp) before the ticket, and the last CTA's reads after it -- one instruction instead of two full fences
+EXB_D unsigned ticket_acq_rel(unsigned* counter) {
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
 }
 
 // ---- register window (window.cuh): the rare, out-of-line halves --------------------------------
@@ -376,7 +520,7 @@ __device__ __noinline__ Window prod_slow_group(Window w, unsigned col, unsigned 
         unsigned hi[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) hi[k] = (unsigned)__double2hiint(__dmul_rn(xa[k], xb[k]));
-        win_after_slow_group<4>(w, mine, hi, false, [&](double v) { deposit(col, stride, v, status); });
+        win_after_slow_group<4>(w, mine, hi, false, [&](double v) { deposit_sum(col, stride, v, status); });
     }
     w.st = status;
     return w;
@@ -388,7 +532,7 @@ __device__ __noinline__ Window win_flush_products(Window w, unsigned col, unsign
     unsigned status = w.st;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (out[k] != 0.0) deposit(col, stride, out[k], status);
+        if (out[k] != 0.0) deposit_sum(col, stride, out[k], status);
     w.st = status;
     return w;
 }
@@ -403,7 +547,7 @@ __device__ __noinline__ Window sum_slow_group(Window w, unsigned col, unsigned s
     deposit(col, stride, x3, status);
     const unsigned hi[4] = {(unsigned)__double2hiint(x0), (unsigned)__double2hiint(x1), (unsigned)__double2hiint(x2),
                             (unsigned)__double2hiint(x3)};
-    win_after_slow_group<4>(w, mine, hi, true, [&](double v) { deposit(col, stride, v, status); });
+    win_after_slow_group<4>(w, mine, hi, true, [&](double v) { deposit_sum(col, stride, v, status); });
     w.st = status;
     return w;
 }
@@ -414,7 +558,7 @@ __device__ __noinline__ Window win_flush_singles(Window w, unsigned col, unsigne
     unsigned status = w.st;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (out[k] != 0.0) deposit(col, stride, out[k], status);
+        if (out[k] != 0.0) deposit_sum(col, stride, out[k], status);
     w.st = status;
     return w;
 }
@@ -426,34 +570,251 @@ __device__ __noinline__ Window win_flush_singles(Window w, unsigned col, unsigne
 constexpr int kBypassTiles = 32;
 constexpr int kBypassMax = 4096;
 
-// Everything after the vector body, shared by the streaming kernels: the scalar part (alignment head, tail, or
-// the whole strided vector), the flush of the expansions, the block merge, and the last CTA's global merge,
-// (optional) peer exchange, rounding and publication.  `body` = elements the vector body has consumed.
+// The fused limb exchange (see Mailbox): send this rank's normalised limbs + status to every rank's mailbox, collect
+// every rank's words of this epoch from MY mailbox, sum, normalise.  Out of line: single-GPU launches never fetch it.
+__device__ __noinline__ bool peer_exchange(const ReduceParams& prm, WarpLimbs& x, unsigned& final_status, const unsigned ln) {
+    const unsigned set = (unsigned)(prm.epoch & 1ull);
+    const unsigned long long tag = peer_tag(prm.epoch) << kDigits;
+    // my words: lane l owns word l (limb l) and, for l < 9, word 32 + l (limbs 32..37, limb 38 low / high, status)
+    const long long top = __shfl_sync(kFullWarp, x.b, 6);
+    unsigned long long w0 = (unsigned long long)x.a, w1 = 0ull;
+    if (ln < 6u) w1 = (unsigned long long)x.b;
+    else if (ln == 6u) w1 = (unsigned long long)top & (unsigned long long)kLimbMask;
+    else if (ln == 7u) w1 = (unsigned long long)(top >> kDigits) & (unsigned long long)kLimbMask;
+    else if (ln == 8u) w1 = (unsigned long long)final_status;
+    for (int r = 0; r < prm.nranks; ++r) {
+        unsigned long long* dst = prm.peers[r]->slot[set][prm.rank].data;
+        st_relaxed_sys(dst + ln, tag | w0);
+        if (ln < 9u) st_relaxed_sys(dst + 32 + ln, tag | w1);
+    }
+    // collect every rank's words of this epoch from MY mailbox
+    const unsigned long long t0 = globaltimer_ns();
+    bool timed_out = false;
+    unsigned long long s0 = 0ull, s1 = 0ull;          // sums over ranks of word ln / word 32 + ln
+    long long s1_signed = 0;
+    for (int r = 0; r < prm.nranks; ++r) {
+        const unsigned long long* src = prm.peers[prm.rank]->slot[set][r].data;
+        unsigned long long v0, v1 = tag;
+        unsigned spins = 0;
+        for (;;) {
+            v0 = ld_relaxed_sys(src + ln);
+            if (ln < 9u) v1 = ld_relaxed_sys(src + 32 + ln);
+            if ((v0 >> kDigits) == (tag >> kDigits) && (v1 >> kDigits) == (tag >> kDigits)) break;
+            if (((++spins) & 63u) == 0u && prm.peer_timeout_ns != 0ull && globaltimer_ns() - t0 > prm.peer_timeout_ns) {
+                timed_out = true;
+                break;
+            }
+        }
+        if (timed_out) break;
+        s0 += v0 & (unsigned long long)kLimbMask;
+        const unsigned long long p1 = v1 & (unsigned long long)kLimbMask;
+        if (ln == 7u) s1_signed += ((long long)(p1 << 12)) >> 12;      // sign-extend the 52-bit field
+        else if (ln == 8u) s1 |= p1;                                    // status flags: OR
+        else s1 += p1;
+    }
+    timed_out = __any_sync(kFullWarp, timed_out);
+    const long long top_lo = (long long)__shfl_sync(kFullWarp, s1, 6);
+    const long long top_hi = __shfl_sync(kFullWarp, s1_signed, 7);
+    unsigned stm = (unsigned)__shfl_sync(kFullWarp, s1, 8);
+    if (timed_out) stm |= kStPeerTimeout;
+    x.a = (long long)s0;                               // <= 8 normalised limbs: no overflow
+    x.b = ln < 6u ? (long long)s1 : (ln == 6u ? top_lo + (top_hi << kDigits) : 0ll);
+    final_status = stm;
+    return warp_normalize(x, ln);
+}
+
+// Steps 4 and 5 of the epilogue (see reduce_finish), shared by every reduction kernel of this file:
+//   4. block merge: split row sums -> one local carry split -> native 64-bit REDs into the global accumulator ->
+//      ticket (skipped by a `solo` CTA, which publishes straight from shared memory);
+//   5. the last CTA's closing WARP: gather, warp-parallel normalise, (optional) peer exchange, round, publish.
+// Not inlined: one copy of this (cold, run-once) code serves all kernels, which keeps them small.
+__device__ __noinline__ void block_merge_and_close(const ReduceParams& prm, const unsigned stride, const unsigned smem_base,
+                                                   const unsigned T, const unsigned tid, unsigned status, const bool solo,
+                                                   long long* block_lo, int* block_hi, unsigned* block_status) {
+    __syncthreads();                                       // block_status initialised; all columns final
+    if (status) {
+        if (solo) atomicOr(block_status, status);
+        else atomicOr(&prm.ws->status, status);
+    }
+    const unsigned warp = tid >> 5, ln = tid & 31u, nwarps = T >> 5;
+#pragma unroll 1
+    for (unsigned j = warp; j < (unsigned)kLimbs; j += nwarps) {      // (rolled on purpose: this code runs once, from a cold instruction cache)
+        long long lo;
+        int hi;
+        row_sum_split(smem_base + j * stride, T, ln, lo, hi);
+        if (ln == 0) {
+            block_lo[j] = lo;
+            block_hi[j] = hi;
+        }
+    }
+    __syncthreads();
+    EXB_PHASE(5);
+    if (warp != 0) return;                                 // the rest is one warp's work
+
+    // limb j of this CTA's sum = lo[j] + hi[j-1]  (|.| < 2^62), spread over the warp
+    WarpLimbs x;
+    x.a = block_lo[ln] + (ln > 0 ? (long long)block_hi[ln - 1] : 0ll);
+    x.b = ln < 7u ? block_lo[32 + ln] + (long long)block_hi[31 + ln] : 0ll;
+    if (ln == 6u) x.b += ((long long)block_hi[38]) << kDigits;     // carry-save bits of the top limb stay in the top limb
+    unsigned final_status = 0;
+    bool last = solo;
+    if (!solo) {
+        // one local split keeps every contribution below 2^52 + 2^10 in magnitude, so that <= 2048 CTAs (and a
+        // pending normalised partial sum) cannot overflow a 64-bit global limb; no carry chain needed here
+        WarpLimbs c, u;
+        c.a = x.a >> kDigits;
+        x.a &= kLimbMask;
+        c.b = ln < 6u ? (x.b >> kDigits) : 0;
+        if (ln < 6u) x.b &= kLimbMask;
+        u = wl_shift_up(c, ln);
+        x.a += u.a;
+        if (ln < 7u) x.b += u.b;
+        if (x.a != 0) atomicAdd(&prm.ws->gacc[ln], (unsigned long long)x.a);
+        if (ln < 7u && x.b != 0) atomicAdd(&prm.ws->gacc[32 + ln], (unsigned long long)x.b);
+        __syncwarp();
+        unsigned ticket = 0;
+        if (ln == 0) ticket = ticket_acq_rel(&prm.ws->counter);
+        ticket = __shfl_sync(kFullWarp, ticket, 0);
+        last = (ticket == gridDim.x - 1);
+    }
+    EXB_PHASE(6);
+    if (!last) return;
+
+    // ---------------- 5. closing warp: normalise the global accumulator, exchange, round, publish ----
+    if (!solo) {
+        x.a = (long long)atomicExch(&prm.ws->gacc[ln], 0ull);
+        x.b = ln < 7u ? (long long)atomicExch(&prm.ws->gacc[32 + ln], 0ull) : 0ll;
+        if (ln == 0) {
+            final_status = prm.finalize && !prm.keep ? atomicExch(&prm.ws->status, 0u) : atomicOr(&prm.ws->status, 0u);
+            prm.ws->counter = 0;
+        }
+    } else {
+        if (ln == 0) final_status = *block_status;
+    }
+    final_status = __shfl_sync(kFullWarp, final_status, 0);
+    bool neg = warp_normalize(x, ln);
+    EXB_PHASE(7);
+    // ---- fused multi-GPU exchange over peer memory (only the closing launch of a reduction) ----
+    if (prm.finalize && prm.nranks > 1) neg = peer_exchange(prm, x, final_status, ln);
+    EXB_PHASE(8);
+    if (prm.finalize) {
+        Result* out = prm.out;
+        const double v = warp_value(x, neg, final_status, prm.round_mode, ln);
+        out->limbs[ln] = x.a;
+        if (ln < 7u) out->limbs[32 + ln] = x.b;
+        if (ln < (unsigned)kFlagSlots) out->flagcnt[ln] = (final_status >> ln) & 1u;
+        if (ln == 0) {
+            out->value = v;
+            out->status = final_status;
+        }
+    }
+    // leave the (normalised) partial sum in the workspace unless this call closes the reduction
+    if (!solo && (!prm.finalize || prm.keep)) {
+        prm.ws->gacc[ln] = (unsigned long long)x.a;
+        if (ln < 7u) prm.ws->gacc[32 + ln] = (unsigned long long)x.b;
+    }
+    EXB_PHASE(9);
+}
+
+// Everything after the unrolled vector body, shared by the streaming kernels:
+//   1. the REMAINDER of the vector region (whatever the equal-sized tiles of the body left over -- for vectors
+//      below ~2^21 elements that is everything): guarded 256-bit loads, four in flight per thread, spread evenly
+//      over all threads of the grid;
+//   2. the scalar part: alignment head, the last n mod 4 elements, or the whole vector when it is strided /
+//      misaligned;
+//   3. the flush of the expansions;
+//   4. the block merge: split row sums (no bound_column pass) -> one local carry split -> native 64-bit REDs into
+//      the global accumulator -> ticket;
+//   5. the last CTA's closing WARP: gather, warp-parallel normalise, (optional) peer exchange, round, publish.
+// `body_vecs` = vectors the body has consumed; `since_norm` = deposits into this thread's column since it was
+// last bounded; `bypass_hint` = the body ended in thrash-bypass mode (its data overflows the expansion).
 template <int F, bool EE, bool DOT>
 EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsigned stride, const unsigned smem_base,
-                         const unsigned T, const unsigned tid, const long long body,
-                         double (&a)[F > 0 ? F : 1][expansions(F)], unsigned status) {
+                         const unsigned T, const unsigned tid, const long long body_vecs,
+                         double (&a)[F > 0 ? F : 1][expansions(F)], unsigned status, int since_norm, bool bypass_hint) {
     constexpr int kM = expansions(F);
     constexpr int kDepPerElem = DOT ? 2 : 1;               // at most one deposit per summand
-    __shared__ long long block_limbs[kLimbs];
-    __shared__ unsigned is_last;
+    constexpr int kSlack = 2 * kM * (F + 2) + 16;          // room for the flush of the expansions
+    __shared__ long long block_lo[kLimbs];
+    __shared__ int block_hi[kLimbs];
     __shared__ unsigned block_status;
     // Latency regime: a single CTA reducing into an empty workspace publishes straight from shared
     // memory -- no global atomics, fence or ticket.
     const bool solo = (gridDim.x == 1) && prm.fresh && prm.finalize;
     if (tid == 0) block_status = 0;
+    EXB_PHASE(2);
 
-    // ---------------- scalar part: alignment head, tail, or the whole strided vector ----------
+    // ---------------- 1. remainder of the vector region ----------------
     {
+        const long long nrem = prm.nvec - body_vecs;
+        const long long gthreads = (long long)gridDim.x * T;
+        long long r = (long long)blockIdx.x * T + tid;
+        if (r < nrem) {
+            constexpr int UR = DOT ? 2 : 4;               // vectors in flight per thread and stream (same bytes for both)
+            const double* pa = prm.a + prm.head + 4 * (body_vecs + r);
+            const double* pb = DOT ? prm.b + prm.head + 4 * (body_vecs + r) : nullptr;
+            const long long vstep = 4 * gthreads;
+            Vec4 va[UR];
+            Vec4 vb[DOT ? UR : 1];
+            bool direct = (F > 0) && prm.adaptive && bypass_hint;
+            int fell = 0;
+#pragma unroll
+            for (int u = 0; u < UR; ++u)
+                if (r + u * gthreads < nrem) {
+                    va[u] = ldg256(pa + u * vstep);
+                    if (DOT) vb[DOT ? u : 0] = ldg256(pb + u * vstep);
+                }
+            for (; r < nrem; r += UR * gthreads) {
+                pa += UR * vstep;
+                if (DOT) pb += UR * vstep;
+#pragma unroll
+                for (int u = 0; u < UR; ++u) {
+                    if (r + u * gthreads < nrem) {
+                        double x4[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                        if (DOT) {
+                            const double y4[4] = {vb[DOT ? u : 0].x, vb[DOT ? u : 0].y, vb[DOT ? u : 0].z, vb[DOT ? u : 0].w};
+                            if (F == 0 || direct) {
+                                double none[1][expansions(0)];
+                                mul_add4<0, false, false>(col, stride, none, status, x4, y4);
+                            } else {
+                                fell += mul_add4<F, EE, false>(col, stride, a, status, x4, y4);
+                            }
+                        } else if (F == 0 || direct) {
+                            deposit4<false>(col, stride, x4[0], x4[1], x4[2], x4[3], status);
+                        } else {
+                            fell += add4<F, EE, false>(col, stride, a, status, x4);
+                        }
+                        if (r + (u + UR) * gthreads < nrem) {
+                            va[u] = ldg256(pa + u * vstep);
+                            if (DOT) vb[DOT ? u : 0] = ldg256(pb + u * vstep);
+                        }
+                    }
+                }
+                // thrash control as in the body, but per thread (lanes are not converged here): once a quarter of this
+                // thread's summands fall off the last level, it deposits the rest of its (short) remainder directly
+                if (F > 0 && prm.adaptive && 4 * fell >= 4 * UR * kDepPerElem) direct = true;
+                fell = 0;
+                since_norm += 4 * UR * kDepPerElem;
+                if (since_norm > kMaxDepositsPerNormalize - 4 * UR * kDepPerElem - kSlack) {
+                    bound_column(col, stride);
+                    since_norm = 0;
+                }
+            }
+        }
+    }
+    EXB_PHASE(3);
+
+    // ---------------- 2. scalar part: alignment head, tail, or the whole strided vector ----------
+    {
+        const long long body = 4 * prm.nvec;               // elements of the vector region
         const long long nscalar = prm.n - body;            // head + tail (or everything)
         const long long gthreads = (long long)gridDim.x * T;
-        int since_norm = 0;
         long long k = (long long)blockIdx.x * T + tid;
-        // Strided vectors (inca / incb != 1: no vector body at all) and long tails: eight independent
-        // loads per thread in flight, consumed four at a time through the same four-summand code as
-        // the vector body (per-thread early exit: lanes need not be converged here).  A warp load of
-        // 32 consecutive elements touches 32 * inc * 8 bytes, so the useful fraction of every sector
-        // is 1 / inc whatever is done here; what this loop buys is memory-level parallelism.
+        // Strided vectors (inca / incb != 1: no vector region at all): eight independent loads per thread in
+        // flight, consumed four at a time through the same four-summand code as the vector body (per-thread early
+        // exit: lanes need not be converged here).  A warp load of 32 consecutive elements touches 32 * inc * 8
+        // bytes, so the useful fraction of every sector is 1 / inc whatever is done here; what this loop buys is
+        // memory-level parallelism.
         for (; k + 7 * gthreads < nscalar; k += 8 * gthreads) {
             double xa[8], xb[DOT ? 8 : 1];
 #pragma unroll
@@ -461,13 +822,13 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
                 const long long kk = k + j * gthreads;
                 const long long idx = kk < prm.head ? kk : kk + body;
                 xa[j] = ldg64(prm.a + idx * prm.inca);
-                if (DOT) xb[j] = ldg64(prm.b + idx * prm.incb);
+                if (DOT) xb[DOT ? j : 0] = ldg64(prm.b + idx * prm.incb);
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 double x4[4] = {xa[4 * h], xa[4 * h + 1], xa[4 * h + 2], xa[4 * h + 3]};
                 if (DOT) {
-                    const double y4[4] = {xb[4 * h], xb[4 * h + 1], xb[4 * h + 2], xb[4 * h + 3]};
+                    const double y4[4] = {xb[DOT ? 4 * h : 0], xb[DOT ? 4 * h + 1 : 0], xb[DOT ? 4 * h + 2 : 0], xb[DOT ? 4 * h + 3 : 0]};
                     mul_add4<F, EE, false>(col, stride, a, status, x4, y4);
                 } else if (F == 0) {
                     deposit4<false>(col, stride, x4[0], x4[1], x4[2], x4[3], status);
@@ -476,7 +837,7 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
                 }
             }
             since_norm += 8 * kDepPerElem;
-            if (since_norm > kMaxDepositsPerNormalize - 8 * kDepPerElem - 2 * kM * (F + 2)) {
+            if (since_norm > kMaxDepositsPerNormalize - 8 * kDepPerElem - kSlack) {
                 bound_column(col, stride);
                 since_norm = 0;
             }
@@ -486,135 +847,21 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
             if (DOT) mul_add1<F, EE>(col, stride, a, status, prm.a[idx * prm.inca], prm.b[idx * prm.incb]);
             else add1<F, EE>(col, stride, a, status, prm.a[idx * prm.inca]);
             since_norm += kDepPerElem;
-            if (since_norm > kMaxDepositsPerNormalize - kDepPerElem - 2 * kM * (F + 2)) {
+            if (since_norm > kMaxDepositsPerNormalize - kDepPerElem - kSlack) {
                 bound_column(col, stride);
                 since_norm = 0;
             }
         }
     }
+    // ---------------- 3. flush the expansions (exact sums of in-range inputs: deposit_sum) ----------
     if (F > 0) {
 #pragma unroll
         for (int i = 0; i < F; ++i)
 #pragma unroll
-            for (int m = 0; m < kM; ++m) deposit(col, stride, a[i][m], status);
+            for (int m = 0; m < kM; ++m) deposit_sum(col, stride, a[i][m], status);
     }
-    bound_column(col, stride);
-    __syncthreads();                                       // block_status initialised; all columns final
-    if (status) {
-        if (solo) atomicOr(&block_status, status);
-        else atomicOr(&prm.ws->status, status);
-    }
-
-    // ---------------- block merge: 39 row sums -> normalise -> global accumulator --------------
-    {
-        const unsigned warp = tid >> 5, ln = tid & 31u, nwarps = T >> 5;
-        for (unsigned j = warp; j < (unsigned)kLimbs; j += nwarps) {
-            const long long s = row_sum(smem_base + j * stride, T, ln);   // |s| < T * (2^52 + 2^11) < 2^62
-            if (ln == 0) block_limbs[j] = s;
-        }
-        __syncthreads();
-        if (!solo) {
-            if (tid == 0) normalize_shared(block_limbs);
-            __syncthreads();
-            for (unsigned j = tid; j < (unsigned)kLimbs; j += T) {
-                const long long v = block_limbs[j];
-                if (v != 0) atomicAdd(&prm.ws->gacc[j], (unsigned long long)v);
-            }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                const unsigned ticket = atomicAdd(&prm.ws->counter, 1u);
-                is_last = (ticket == gridDim.x - 1);
-            }
-            __syncthreads();
-        }
-    }
-
-    // ---------------- last CTA: normalise the global accumulator, publish ----------------------
-    if (solo || is_last) {
-        if (!solo) {
-            __threadfence();
-            for (unsigned j = tid; j < (unsigned)kLimbs; j += T)
-                block_limbs[j] = (long long)atomicExch(&prm.ws->gacc[j], 0ull);
-            __syncthreads();
-        }
-        __shared__ unsigned final_status;
-        if (tid == 0) {
-            unsigned st;
-            if (solo) st = block_status;
-            else st = prm.finalize && !prm.keep ? atomicExch(&prm.ws->status, 0u) : atomicOr(&prm.ws->status, 0u);
-            normalize_shared(block_limbs);
-            final_status = st;
-        }
-        __syncthreads();
-        // ---- fused multi-GPU exchange over peer memory (only the closing launch of a reduction) ----
-        if (prm.finalize && prm.nranks > 1) {
-            const unsigned set = (unsigned)(prm.epoch & 1ull);
-            const unsigned st = final_status;
-            for (unsigned j = tid; j < (unsigned)kMsgWords * (unsigned)prm.nranks; j += T) {
-                const unsigned r = j / kMsgWords, w = j % kMsgWords;
-                const unsigned long long v = w < (unsigned)kLimbs ? (unsigned long long)block_limbs[w]
-                                                                  : (unsigned long long)((st >> (w - kLimbs)) & 1u);
-                st_relaxed_sys(&prm.peers[r]->slot[set][prm.rank].data[w], v);
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid < (unsigned)prm.nranks) st_release_sys(&prm.peers[tid]->slot[set][prm.rank].seq, prm.epoch);
-            // wait for every rank's contribution of this epoch in MY mailbox (bounded spin)
-            __shared__ unsigned timed_out;
-            if (tid == 0) timed_out = 0;
-            __syncthreads();
-            if (tid < (unsigned)prm.nranks) {
-                const unsigned long long* seq = &prm.peers[prm.rank]->slot[set][tid].seq;
-                const long long t0 = clock64();
-                while (ld_acquire_sys(seq) != prm.epoch) {
-                    if (clock64() - t0 > 20000000000ll) {        // ~10 s: a peer never arrived
-                        atomicOr(&timed_out, 1u);
-                        break;
-                    }
-                    __nanosleep(200);
-                }
-            }
-            __syncthreads();
-            __shared__ unsigned long long merged[kMsgWords];
-            for (unsigned w = tid; w < (unsigned)kMsgWords; w += T) {
-                unsigned long long sum = 0;
-                for (int r = 0; r < prm.nranks; ++r) sum += ld_relaxed_sys(&prm.peers[prm.rank]->slot[set][r].data[w]);
-                merged[w] = sum;                                 // <= 8 normalised limbs: no overflow
-            }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned stm = timed_out ? kStPeerTimeout : 0u;
-                for (int k = 0; k < kFlagSlots; ++k)
-                    if (merged[kLimbs + k] != 0) stm |= 1u << k;
-                for (int j = 0; j < kLimbs; ++j) block_limbs[j] = (long long)merged[j];
-                normalize_shared(block_limbs);
-                final_status = stm;
-            }
-            __syncthreads();
-        }
-        if (tid == 0) {
-            const unsigned st = final_status;
-            const bool neg = block_limbs[kLimbs - 1] < 0;
-            if (prm.finalize) {
-                Result* out = prm.out;
-                for (int j = 0; j < kLimbs; ++j) out->limbs[j] = block_limbs[j];
-                double v;
-                if ((st & kStNaN) || ((st & kStPosInf) && (st & kStNegInf))) v = __longlong_as_double(0x7ff8000000000000ll);
-                else if (st & kStPosInf) v = __longlong_as_double(0x7ff0000000000000ll);
-                else if (st & kStNegInf) v = __longlong_as_double(0xfff0000000000000ll);
-                else v = prm.round_mode ? round_exact(block_limbs, neg) : round_ref_compat(block_limbs, neg);
-                out->value = v;
-                out->status = st;
-                for (int k = 0; k < kFlagSlots; ++k) out->flagcnt[k] = (st >> k) & 1u;
-            }
-            if (!solo) prm.ws->counter = 0;
-        }
-        __syncthreads();
-        // leave the (normalised) partial sum in the workspace unless this call closes the reduction
-        if (!solo && (!prm.finalize || prm.keep))
-            for (unsigned j = tid; j < (unsigned)kLimbs; j += T) prm.ws->gacc[j] = (unsigned long long)block_limbs[j];
-    }
+    EXB_PHASE(4);
+    block_merge_and_close(prm, stride, smem_base, T, tid, status, solo, block_lo, block_hi, &block_status);
 }
 
 // (Measured and rejected, round 1: moving the thrash bypass or the expansion walk of THIS kernel into out-of-line
@@ -622,7 +869,7 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
 // residuals), and a function that is itself called and calls on spills its prefetch slots: 1.9 instead of
 // 6.0 TB/s on narrow data; a call to an out-of-line bypass from inside this loop cost the walk 40 %.)
 template <int F, bool EE, bool DOT, int U, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReduceParams prm) {
+__global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_constant__ ReduceParams prm) {
     extern __shared__ long long smem[];
     const unsigned T = blockDim.x;
     const unsigned tid = threadIdx.x;
@@ -630,9 +877,7 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
     const unsigned stride = 8u * T;
     const unsigned col = smem_base + 8u * tid;
 
-    for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
-    // columns are thread-private: no barrier needed before use
-
+    EXB_PHASE(0);
     unsigned status = 0;
     constexpr int kM = expansions(F);
     double a[F > 0 ? F : 1][kM];
@@ -644,11 +889,14 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
     constexpr int kDepPerElem = DOT ? 2 : 1;               // at most one deposit per summand
     constexpr int kDepPerTile = 4 * U * kDepPerElem;
     const long long TILE = (long long)T * 4 * U;
+    int since_norm = 0;
+    bool bypass_hint = false;
 
-    // ---------------- vector body: full tiles, 256-bit loads, rolling prefetch ----------------
-    if (prm.ntiles > 0 && (long long)blockIdx.x < prm.ntiles) {
-        // this CTA owns tiles blockIdx.x, blockIdx.x + grid, ...: `iters` of them
-        const unsigned iters = (unsigned)((prm.ntiles - 1 - blockIdx.x) / gridDim.x) + 1u;
+    // ---------------- vector body: prm.iters full tiles per CTA, 256-bit loads, rolling prefetch ----------------
+    // (every CTA streams the same number of tiles: tiles blockIdx.x, blockIdx.x + grid, ...; what that leaves over
+    // is spread evenly over all threads by reduce_finish)
+    if (prm.iters > 0) {
+        const unsigned iters = (unsigned)prm.iters;
         const long long tile_step = (long long)gridDim.x * TILE;               // elements between my tiles
         const double* pa = prm.a + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4;
         const double* pb = DOT ? prm.b + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4 : nullptr;
@@ -660,7 +908,8 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
             va[u] = ldg256(pa + u * vstep);
             if (DOT) vb[u] = ldg256(pb + u * vstep);
         }
-        int since_norm = 0;
+        // clear the (thread-private: no barrier needed) column while the first loads are in flight
+        for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
         int bypass = 0, backoff = kBypassTiles;
         for (unsigned it = 0; it < iters; ++it) {
             pa += tile_step;
@@ -742,15 +991,17 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const ReducePara
                 }
             }
             since_norm += kDepPerTile;
-            if (since_norm > kMaxDepositsPerNormalize - kDepPerTile - 2 * kM * (F + 2)) {
+            if (since_norm > kMaxDepositsPerNormalize - kDepPerTile - 2 * kM * (F + 2) - 16) {
                 bound_column(col, stride);
                 since_norm = 0;
             }
         }
-        bound_column(col, stride);
+        bypass_hint = bypass > 0;
+    } else {
+        for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
     }
-
-    reduce_finish<F, EE, DOT>(prm, col, stride, smem_base, T, tid, prm.ntiles * TILE, a, status);
+    EXB_PHASE(1);
+    reduce_finish<F, EE, DOT>(prm, col, stride, smem_base, T, tid, prm.iters * (long long)gridDim.x * T * U, a, status, since_norm, bypass_hint);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -803,7 +1054,7 @@ __device__ __noinline__ WindowP<W> prodw_slow_group(WindowP<W> w, unsigned col, 
     }
     gmin = __reduce_min_sync(0xffffffffu, gmin);
     gmax = __reduce_max_sync(0xffffffffu, gmax);
-    winp_cover<W>(w, gmin, gmax, [&](double v) { deposit(col, stride, v, status); });
+    winp_cover<W>(w, gmin, gmax, [&](double v) { deposit_sum(col, stride, v, status); });
     (void)mine;
     w.st = status;
     return w;
@@ -816,7 +1067,7 @@ __device__ __noinline__ WindowP<W> winp_flush(WindowP<W> w, unsigned col, unsign
     unsigned status = w.st;
 #pragma unroll
     for (int k = 0; k <= W; ++k)
-        if (out[k] != 0.0) deposit(col, stride, out[k], status);
+        if (out[k] != 0.0) deposit_sum(col, stride, out[k], status);
     w.st = status;
     return w;
 }
@@ -936,7 +1187,7 @@ __device__ __noinline__ WindowP<W> sumw_slow_group(WindowP<W> w, unsigned col, u
     }
     gmin = __reduce_min_sync(0xffffffffu, gmin);
     gmax = __reduce_max_sync(0xffffffffu, gmax);
-    wins_cover<W>(w, gmin, gmax, [&](double v) { deposit(col, stride, v, status); });
+    wins_cover<W>(w, gmin, gmax, [&](double v) { deposit_sum(col, stride, v, status); });
     w.st = status;
     return w;
 }
@@ -948,7 +1199,7 @@ __device__ __noinline__ WindowP<W> wins_flush(WindowP<W> w, unsigned col, unsign
     unsigned status = w.st;
 #pragma unroll
     for (int k = 0; k <= W; ++k)
-        if (out[k] != 0.0) deposit(col, stride, out[k], status);
+        if (out[k] != 0.0) deposit_sum(col, stride, out[k], status);
     w.st = status;
     return w;
 }
@@ -1017,21 +1268,22 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, 
 }
 
 template <bool DOT, int DW, int DD, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const ReduceParams prm) {
+__global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const __grid_constant__ ReduceParams prm) {
     extern __shared__ long long smem[];
     const unsigned T = blockDim.x;
     const unsigned tid = threadIdx.x;
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned stride = 8u * T;
     const unsigned col = smem_base + 8u * tid;
-    for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+    EXB_PHASE(0);
 
     unsigned status = 0;
     constexpr int kDepPerElem = DOT ? 2 : 1;
     const long long ROW = (long long)T * 4;
+    bool zeroed = false;                                       // (the column is cleared behind the first loads where possible)
 
-    if (prm.ntiles > 0 && (long long)blockIdx.x < prm.ntiles) {
-        const unsigned iters = (unsigned)((prm.ntiles - 1 - blockIdx.x) / gridDim.x) + 1u;     // my rows
+    if (prm.iters > 0) {
+        const unsigned iters = (unsigned)prm.iters;            // my rows: blockIdx.x, blockIdx.x + grid, ... (same count in every CTA)
         const long long row_step = (long long)gridDim.x * ROW;
         const double* pa = prm.a + prm.head + (long long)blockIdx.x * ROW + (long long)tid * 4;  // my first row
         const double* pb = DOT ? prm.b + prm.head + (long long)blockIdx.x * ROW + (long long)tid * 4 : nullptr;
@@ -1039,6 +1291,8 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const ReducePar
         unsigned k = 0;                                        // rows consumed so far
         // (vectors too short for the windows to pay -- fewer than 32 rows per CTA, n < ~2^23 -- go straight to loop 2)
         if constexpr (DW > 0) if (prm.window && iters >= 32u) {
+            for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+            zeroed = true;
             unsigned st1 = 0;
             int range[2] = {4096, -4096};                      // exponents that have missed so far, warp-uniform
             if constexpr (DOT) {
@@ -1074,6 +1328,10 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const ReducePar
 #pragma unroll
         for (int u = 0; u < DD; ++u)
             if (loaded < iters) load_row(u);
+        if (!zeroed) {
+            for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+            zeroed = true;
+        }
         auto consume = [&](int u, bool all_pos) {
             if (DOT) {
                 const double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
@@ -1123,24 +1381,124 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const ReducePar
             if (k + u < iters) consume(u, false);
         bound_column(col, stride);
     }
+    if (!zeroed)
+        for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+    EXB_PHASE(1);
     double none[1][expansions(0)];
-    reduce_finish<0, false, DOT>(prm, col, stride, smem_base, T, tid, prm.ntiles * ROW, none, status);
+    reduce_finish<0, false, DOT>(prm, col, stride, smem_base, T, tid, prm.iters * (long long)gridDim.x * T, none, status, 0, false);
+}
+
+// scalar part of exblas_small_kernel: alignment head, tail, or the whole strided / misaligned vector (four loads in
+// flight).  Out of line so that the usual aligned unit-stride call does not even fetch it.
+template <bool DOT>
+__device__ __noinline__ unsigned small_scalar_part(const ReduceParams& prm, const unsigned col, const unsigned stride,
+                                                   const unsigned tid, const unsigned T) {
+    unsigned status = 0;
+    double none[1][expansions(0)];
+    const long long body = 4 * prm.nvec;
+    const long long nscalar = prm.n - body;
+    for (long long k = tid; k < nscalar; k += 4ll * T) {
+        double xa[4], xb[DOT ? 4 : 1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long kk = k + (long long)j * T;
+            if (kk < nscalar) {
+                const long long idx = kk < prm.head ? kk : kk + body;
+                xa[j] = ldg64(prm.a + idx * prm.inca);
+                if (DOT) xb[DOT ? j : 0] = ldg64(prm.b + idx * prm.incb);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (k + (long long)j * T < nscalar) {
+                if (DOT) mul_add1<0, false>(col, stride, none, status, xa[j], xb[DOT ? j : 0]);
+                else deposit(col, stride, xa[j], status);
+            }
+        }
+    }
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Latency regime (n <= a few thousand elements): ONE CTA, and a kernel that is SMALL.  A reduction of 8 KB is over
+// in the time a streaming kernel spends fetching its own (unrolled, run-once, instruction-cache-cold) code, so this
+// kernel trades every throughput device for short code: up to four 256-bit loads per thread issued first, direct
+// deposits through the out-of-line deposit (one hot copy of the code), no expansions -- fpe never changes the
+// result, and with a handful of summands per thread there is nothing for an expansion to amortise -- no bounding
+// (<= 64 deposits per column), and the shared epilogue published straight from shared memory.
+// The host guarantees nvec <= 4 * T and a fresh, closing launch (solo).
+// ------------------------------------------------------------------------------------------------
+template <bool DOT>
+__global__ void __launch_bounds__(512, 1) exblas_small_kernel(const __grid_constant__ ReduceParams prm) {
+    extern __shared__ long long smem[];
+    __shared__ long long block_lo[kLimbs];
+    __shared__ int block_hi[kLimbs];
+    __shared__ unsigned block_status;
+    const unsigned T = blockDim.x;
+    const unsigned tid = threadIdx.x;
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned stride = 8u * T;
+    const unsigned col = smem_base + 8u * tid;
+    EXB_PHASE(0);
+    Vec4 va[4];
+    Vec4 vb[DOT ? 4 : 1];
+    const long long nvec = prm.nvec;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const long long r = (long long)tid + (long long)u * T;
+        if (r < nvec) {
+            va[u] = ldg256(prm.a + prm.head + 4 * r);
+            if (DOT) vb[DOT ? u : 0] = ldg256(prm.b + prm.head + 4 * r);
+        }
+    }
+    if (tid == 0) block_status = 0;
+#pragma unroll 13
+    for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+    unsigned status = 0;
+    double none[1][expansions(0)];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if ((long long)tid + (long long)u * T < nvec) {
+            const double x4[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (DOT) {
+                    const double y4[4] = {vb[DOT ? u : 0].x, vb[DOT ? u : 0].y, vb[DOT ? u : 0].z, vb[DOT ? u : 0].w};
+                    mul_add1<0, false>(col, stride, none, status, x4[k], y4[k]);
+                } else {
+                    deposit(col, stride, x4[k], status);
+                }
+            }
+        }
+    }
+    EXB_PHASE(1);
+    // scalar part: alignment head, tail, or the whole strided / misaligned vector (out of line: usually absent)
+    if (prm.n != 4 * nvec) status |= small_scalar_part<DOT>(prm, col, stride, tid, T);
+    EXB_PHASE(4);
+    block_merge_and_close(prm, stride, smem_base, T, tid, status, true, block_lo, block_hi, &block_status);
 }
 
 // Multi-GPU epilogue: the result slot's limbs and flag counters have been summed over ranks by an
 // integer all-reduce; normalise, rebuild the status word and round.  Every rank runs this on the
 // same integers, so every rank gets the same bits.
 __global__ void exblas_finalize_kernel(Result* res, int round_mode) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        long long acc[kLimbs];
-        for (int j = 0; j < kLimbs; ++j) acc[j] = res->limbs[j];
-        unsigned st = 0;
-        for (int k = 0; k < kFlagSlots; ++k)
-            if (res->flagcnt[k] != 0) st |= (1u << k);
-        res->value = finalize_value(acc, st, round_mode);
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const unsigned ln = threadIdx.x;
+    WarpLimbs x;
+    x.a = res->limbs[ln];
+    x.b = ln < 7u ? res->limbs[32 + ln] : 0ll;
+    unsigned st = 0;
+    for (int k = 0; k < kFlagSlots; ++k)
+        if (res->flagcnt[k] != 0) st |= (1u << k);
+    const bool neg = warp_normalize(x, ln);
+    const double v = warp_value(x, neg, st, round_mode, ln);
+    __syncwarp();
+    res->limbs[ln] = x.a;
+    if (ln < 7u) res->limbs[32 + ln] = x.b;
+    if (ln < (unsigned)kFlagSlots) res->flagcnt[ln] = (st >> ln) & 1u;
+    if (ln == 0) {
+        res->value = v;
         res->status = st;
-        for (int j = 0; j < kLimbs; ++j) res->limbs[j] = acc[j];
-        for (int k = 0; k < kFlagSlots; ++k) res->flagcnt[k] = (st >> k) & 1u;
     }
 }
 

@@ -77,34 +77,36 @@ EXB_HD bool normalize(long long* acc) {
     return carry < 0;
 }
 
+// x * 2^e for |e| <= 1040 and |x| an integer below 2^64 (what the finalisers need).  On the device the scaling is
+// two multiplications by exact powers of two assembled from the exponent field -- the first one is exact (the
+// intermediate stays normal), so the result is rounded once, exactly like ldexp(), at a fraction of its code size
+// (the epilogue runs once per launch from a cold instruction cache: every instruction counts there).
 EXB_HD double exb_ldexp(double x, int e) {
 #if defined(__CUDA_ARCH__)
-    return ldexp(x, e);
+    const int e1 = e / 2, e2 = e - e1;
+    const double p1 = __longlong_as_double((long long)(e1 + 1023) << 52);
+    const double p2 = __longlong_as_double((long long)(e2 + 1023) << 52);
+    return __dmul_rn(__dmul_rn(x, p1), p2);
 #else
     return std::ldexp(x, e);
 #endif
 }
 
-// Restatement of the reference Round() on normalised limbs (superaccumulator.cpp:80-134).
-// `acc` must already be in normal form; `negative` is normalize()'s return value.
-EXB_HD double round_ref_compat(const long long* acc, bool negative) {
-    int i = kLimbs - 1;
-    while (i >= 0 && acc[i] == 0) --i;                                   // :91-94
-    if (negative) {
-        while (i >= 0 && (acc[i] & kLimbMask) == kLimbMask) --i;         // :95-101
-    }
+// Restatement of the reference Round() (superaccumulator.cpp:80-134), split in two so that the serial
+// (host, one thread) and the warp-parallel (reduce_kernel.cuh: warp_round) scans share the arithmetic:
+//   * the SCAN finds i = the limb Round() starts from (:91-101), and whether the limbs below i-1 hold a
+//     non-zero sticky contribution (:116-119);
+//   * round_ref_parts() is everything else (:102-134, mylibm.hpp:156-171), from the two limbs i, i-1.
+EXB_HD double round_ref_parts(int i, long long acc_i, long long acc_im1, bool sticky_nonzero, bool negative) {
     if (i < 0) return 0.0;                                               // :102-104
-    long long hiword = negative ? kLimbMask - acc[i] : acc[i];           // :106 (one's complement)
+    long long hiword = negative ? kLimbMask - acc_i : acc_i;             // :106 (one's complement)
     double rounded = (double)hiword;
     double hi = exb_ldexp(rounded, (i - kFWords) * kDigits);             // :108
     if (i == 0) return negative ? -hi : hi;                              // :109-111
     hiword -= (long long)rounded;                                        // :112 (rounded is integral)
     double mid = exb_ldexp((double)hiword, (i - kFWords) * kDigits);     // :113
-    long long sticky = 0;
-    for (int j = 0; j != i - 1; ++j)                                     // :116-119
-        sticky |= negative ? (1ll << kDigits) - acc[j] : acc[j];
-    long long loword = negative ? (1ll << kDigits) - acc[i - 1] : acc[i - 1];   // :121
-    loword |= (sticky != 0);                                             // :122
+    long long loword = negative ? (1ll << kDigits) - acc_im1 : acc_im1;  // :121
+    loword |= (long long)sticky_nonzero;                                 // :122
     double lo = exb_ldexp((double)loword, (i - 1 - kFWords) * kDigits);  // :123
     if (mid != 0) {                                                      // :128-130, mylibm.hpp:156-171
         double d = mid + lo;
@@ -124,6 +126,20 @@ EXB_HD double round_ref_compat(const long long* acc, bool negative) {
     return negative ? -hi : hi;
 }
 
+// `acc` must already be in normal form; `negative` is normalize()'s return value.
+EXB_HD double round_ref_compat(const long long* acc, bool negative) {
+    int i = kLimbs - 1;
+    while (i >= 0 && acc[i] == 0) --i;                                   // :91-94
+    if (negative) {
+        while (i >= 0 && (acc[i] & kLimbMask) == kLimbMask) --i;         // :95-101
+    }
+    if (i <= 0) return round_ref_parts(i, i == 0 ? acc[0] : 0, 0, false, negative);
+    long long sticky = 0;
+    for (int j = 0; j != i - 1; ++j)                                     // :116-119
+        sticky |= negative ? (1ll << kDigits) - acc[j] : acc[j];
+    return round_ref_parts(i, acc[i], acc[i - 1], sticky != 0, negative);
+}
+
 EXB_HD int exb_clzll(unsigned long long v) {
 #if defined(__CUDA_ARCH__)
     return __clzll((long long)v);
@@ -134,40 +150,34 @@ EXB_HD int exb_clzll(unsigned long long v) {
 
 // Correctly rounded (nearest, ties to even) value of normalised limbs; handles subnormal
 // results and overflow to +-inf.  Not part of the reference; checked against math.fsum / MPFR.
-EXB_HD double round_exact(const long long* acc, bool negative) {
-    unsigned long long m[kLimbs];      // magnitude, 52-bit digits, top digit unbounded
-    if (!negative) {
-        for (int i = 0; i < kLimbs; ++i) m[i] = (unsigned long long)acc[i];
-    } else {
-        long long borrow = 0;
-        for (int i = 0; i < kLimbs - 1; ++i) {
-            long long v = borrow - acc[i];               // in (-2^52 - 1, 0]
-            borrow = v >> kDigits;
-            m[i] = (unsigned long long)(v - borrow * (1ll << kDigits));
-        }
-        m[kLimbs - 1] = (unsigned long long)(borrow - acc[kLimbs - 1]);
-    }
-    int top = kLimbs - 1;
-    while (top >= 0 && m[top] == 0) --top;
+// Split like round_ref_compat: the scan produces the MAGNITUDE's top three radix-2^52 digits
+// (m_top != 0 at limb index `top`; m1, m2 the two digits below, zero where they do not exist) and
+// whether anything non-zero lies below them; round_exact_parts() does the rest.
+EXB_HD double round_exact_parts(int top, unsigned long long m_top, unsigned long long m1, unsigned long long m2,
+                                bool sticky, bool negative) {
     if (top < 0) return 0.0;
-    const int width = 64 - exb_clzll(m[top]);            // significant bits of the top digit (<= 63)
+    const int width = 64 - exb_clzll(m_top);             // significant bits of the top digit (<= 63)
     const int P = kDigits * top + width - 1;             // MSB position above the limb-0 LSB
     const int e = P - kDigits * kFWords;                 // exponent of the MSB
     // 64-bit window w = bits [P-63, P] of the magnitude (zero filled), sticky = anything below it
-    unsigned long long w = m[top] << (64 - width);
+    unsigned long long w = m_top << (64 - width);
     int filled = width;
-    bool sticky = false;
-    for (int j = top - 1; j >= 0; --j) {
+    const unsigned long long lower[2] = {m1, m2};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 2; ++k) {
+        const unsigned long long mj = lower[k];
         const int room = 64 - filled;
         if (room >= kDigits) {
-            w |= m[j] << (room - kDigits);
+            w |= mj << (room - kDigits);
             filled += kDigits;
         } else if (room > 0) {
-            w |= m[j] >> (kDigits - room);
-            sticky |= (m[j] & ((1ull << (kDigits - room)) - 1ull)) != 0;
+            w |= mj >> (kDigits - room);
+            sticky |= (mj & ((1ull << (kDigits - room)) - 1ull)) != 0;
             filled = 64;
         } else {
-            sticky |= (m[j] != 0);
+            sticky |= (mj != 0);
         }
     }
     int keep = 53;                                       // result bits; fewer when subnormal
@@ -187,6 +197,27 @@ EXB_HD double round_exact(const long long* acc, bool negative) {
     if (round_bit && (sticky || (q & 1ull))) q += 1;
     double r = exb_ldexp((double)q, (P - keep + 1) - kDigits * kFWords);
     return negative ? -r : r;
+}
+
+EXB_HD double round_exact(const long long* acc, bool negative) {
+    unsigned long long m[kLimbs];      // magnitude, 52-bit digits, top digit unbounded
+    if (!negative) {
+        for (int i = 0; i < kLimbs; ++i) m[i] = (unsigned long long)acc[i];
+    } else {
+        long long borrow = 0;
+        for (int i = 0; i < kLimbs - 1; ++i) {
+            long long v = borrow - acc[i];               // in (-2^52 - 1, 0]
+            borrow = v >> kDigits;
+            m[i] = (unsigned long long)(v - borrow * (1ll << kDigits));
+        }
+        m[kLimbs - 1] = (unsigned long long)(borrow - acc[kLimbs - 1]);
+    }
+    int top = kLimbs - 1;
+    while (top >= 0 && m[top] == 0) --top;
+    if (top < 0) return 0.0;
+    bool sticky = false;
+    for (int j = top - 3; j >= 0; --j) sticky |= (m[j] != 0);
+    return round_exact_parts(top, m[top], top >= 1 ? m[top - 1] : 0ull, top >= 2 ? m[top - 2] : 0ull, sticky, negative);
 }
 
 // Exact accumulation of one double into a plain limb array (not the hot path: used where a value
@@ -361,6 +392,32 @@ __device__ __noinline__ unsigned deposit_any(unsigned col, unsigned stride, unsi
 }
 EXB_D void deposit(unsigned col, unsigned stride, double x, unsigned& status) {
     status |= deposit_any(col, stride, (unsigned)__double2loint(x), (unsigned)__double2hiint(x));
+}
+
+// Deposit of an INTERNAL partial sum (an expansion level at flush time, a drained window digit).  Every input is
+// below 2^988, but the sum of several of them inside one expansion need not be; the superaccumulator-only path
+// adds the same inputs into limb 38 digit by digit without complaint, so the result must not depend on fpe here.
+// Finite values in [2^988, 2^995) are therefore added to limb 38 (weight 2^936) as integers (< 2^59 each, and a
+// flush deposits at most eight of them); only beyond that -- where limb 38 itself is about to overflow -- is the
+// value dropped and flagged.
+__device__ __noinline__ unsigned deposit_sum_any(unsigned col, unsigned stride, unsigned lo, unsigned hi) {
+    if (in_fast_range(hi)) {
+        deposit_fast(col, stride, lo, hi);
+        return 0u;
+    }
+    const unsigned ahi = hi & 0x7fffffffu;
+    const unsigned E = ahi >> 20;
+    if (E >= kELim && E < kELim + 7u) {
+        const unsigned long long mant = ((unsigned long long)((ahi & 0xfffffu) | 0x100000u) << 32) | lo;
+        const unsigned long long v = mant << (E - kELim);             // units of 2^936
+        const unsigned a38 = col + (unsigned)(kLimbs - 1) * stride;
+        sts64(a38, (hi >> 31) ? lds64(a38) - v : lds64(a38) + v);
+        return 0u;
+    }
+    return deposit_slow(col, stride, lo, hi);
+}
+EXB_D void deposit_sum(unsigned col, unsigned stride, double x, unsigned& status) {
+    status |= deposit_sum_any(col, stride, (unsigned)__double2loint(x), (unsigned)__double2hiint(x));
 }
 
 // Four independent doubles; one range test for all of them (the common case is all-fast).

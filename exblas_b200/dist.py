@@ -6,7 +6,7 @@ its shard to 39 normalised int64 limbs on its GPU, the ranks sum those limbs as 
 order-free), and every rank normalises and rounds the same integers -- so all ranks, and any
 number of ranks, return identical bits.
 
-Three transports for the 44 x int64 message (39 limbs + 5 status-flag counters):
+Three transports for the message (39 limbs + status flags; 44 x int64 for the all-reduce variants):
   * `init_peer()`            -- FUSED: the closing reduction kernel stores the message into every
     peer's mailbox over NVLink peer memory and merges what it receives, no collective call at all
     (exblas_b200_peer_export / exblas_b200_peer_attach);
@@ -94,6 +94,8 @@ class DistributedReducer:
         self.handle = handle
         self._nccl_ready = False
         self.fused = False
+        if handle is not None and self.world > 1:
+            handle.set_option("world_size", self.world)      # the C ABI then refuses to finish a reduction locally
 
     def init_nccl(self) -> None:
         """Create the C-ABI NCCL communicator: rank 0 makes the unique id, everyone gets it through
@@ -130,7 +132,15 @@ class DistributedReducer:
         ok = all(flags)
         self.handle.set_option("fused_allreduce", 1 if ok else 0)
         self.fused = ok
+        if not ok:
+            self.init_nccl()             # never leave a multi-rank reducer without a transport (collective: all ranks get here)
         return ok
+
+    def _require_transport(self) -> None:
+        if self.world > 1 and not (self.fused or self._nccl_ready):
+            raise blas1.ExblasB200Error(
+                f"DistributedReducer: {self.world} ranks but no transport -- call init_peer() or init_nccl() "
+                "collectively first (a reduction now would return this rank's shard only)")
 
     # device-resident shard in, identical value on every rank out
     def exsum(self, n_local: int, d_a, fpe: int = 0, early_exit: bool = False, round_mode: int = ROUND_REFERENCE):
@@ -138,6 +148,7 @@ class DistributedReducer:
         return self.handle.fetch()
 
     def exsum_async(self, n_local, d_a, fpe=0, early_exit=False, round_mode=ROUND_REFERENCE):
+        self._require_transport()
         self.handle.exsum_async(n_local, d_a, 1, 0, fpe, early_exit, round_mode)
         if self.world > 1:
             self.handle.allreduce_async(round_mode)
@@ -147,6 +158,7 @@ class DistributedReducer:
         return self.handle.fetch()
 
     def exdot_async(self, n_local, d_a, d_b, fpe=0, early_exit=False, round_mode=ROUND_REFERENCE):
+        self._require_transport()
         self.handle.exdot_async(n_local, d_a, 1, 0, d_b, 1, 0, fpe, early_exit, round_mode)
         if self.world > 1:
             self.handle.allreduce_async(round_mode)

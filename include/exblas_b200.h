@@ -45,6 +45,7 @@ extern "C" {
 #define EXBLAS_B200_ENOGPU (-3)       /* no usable sm_100 device */
 #define EXBLAS_B200_ENCCL (-4)        /* NCCL missing or a NCCL call failed */
 #define EXBLAS_B200_ENOMEM (-5)
+#define EXBLAS_B200_EPEER (-6)        /* fused multi-GPU exchange: a peer did not arrive in time (see peer_attach) */
 
 /* data status flags (bitwise OR), returned by exblas_b200_last_status() */
 #define EXBLAS_B200_ST_NAN 1u         /* NaN met: value is NaN */
@@ -52,7 +53,8 @@ extern "C" {
 #define EXBLAS_B200_ST_NEGINF 4u      /* -Inf met */
 #define EXBLAS_B200_ST_TOOLARGE 8u    /* finite |x| (or product) >= 2^988: outside the 39-limb layout, dropped */
 #define EXBLAS_B200_ST_TOOSMALL 16u   /* bits below 2^-1040 truncated: result not exact */
-#define EXBLAS_B200_ST_PEERTIMEOUT 32u /* fused multi-GPU exchange: a peer never arrived; result is partial */
+#define EXBLAS_B200_ST_PEERTIMEOUT 32u /* fused multi-GPU exchange: a peer never arrived; the value is NaN, the limbs are
+                                          partial and exblas_b200_fetch / the synchronous calls return EXBLAS_B200_EPEER */
 
 typedef struct exblas_b200_handle_s* exblas_b200_handle_t;
 
@@ -66,13 +68,19 @@ int exblas_b200_destroy(exblas_b200_handle_t handle);
  * legacy default stream (NULL), like cuBLAS: ordered after prior default-stream work of the process. */
 int exblas_b200_set_stream(exblas_b200_handle_t handle, void* stream);
 
-/* Tuning knobs (performance only, never the result): "block_threads" (multiple of 32, <= 512),
- * "blocks" (0 = one per SM), "host_chunk_elems", "gemv_parts" (0 = automatic column split, <= 1024),
+/* Tuning knobs (performance only, never the result): "block_threads" (multiple of 32, <= 512) and
+ * "blocks" (0 = automatic) fix the launch shape by hand ("auto_shape" = 1 returns to the size-dependent
+ * one: a single CTA up to "solo_max_elems" elements, 256-thread CTAs up to "small_max_elems", else one
+ * 512-thread CTA per SM), "host_chunk_elems", "host_threads", "gemv_parts" (0 = automatic column split, <= 1024),
  * "adaptive" (1 = a warp bypasses the expansion and deposits straight into its superaccumulators while
  * the expansion overflows on most elements; 0 = always walk all fpe levels, as the reference kernels do),
  * "window" (register window of the superaccumulator-only kernels: 0 off, 1 narrow windows, 2 narrow then
  * wide windows (default), 3 wide only), "gemv_n_shape" (0..2) / "gemv_t_shape" (0..3): launch shapes of
- * the ExGEMV window kernels, "fused_allreduce" (1 = exchange limbs inside the kernel once peers are attached). */
+ * the ExGEMV window kernels, "fused_allreduce" (1 = exchange limbs inside the kernel once peers are attached),
+ * "world_size" (declares a multi-rank job: exblas_b200_allreduce_async then fails with EXBLAS_B200_ENCCL
+ * instead of finishing locally when no transport covers that many ranks),
+ * "peer_timeout_ms" (fused exchange: how long a rank waits for its peers, default 600000, 0 = for ever),
+ * "phase_timing" (diagnostics: per-CTA globaltimer stamps, read with exblas_b200_phase_times). */
 int exblas_b200_set_option(exblas_b200_handle_t handle, const char* name, int64_t value);
 
 /* ---- synchronous entry points: the ones a reference binding calls --------------------------- */
@@ -172,7 +180,12 @@ int exblas_b200_allreduce_async(exblas_b200_handle_t handle, int round_mode);
  * *_async reduction on this handle is a COLLECTIVE: all ranks must issue the same sequence of
  * reductions; each ends with identical value / limbs / status on every rank, and
  * exblas_b200_allreduce_async becomes a no-op.  Option "fused_allreduce" = 0 switches back to NCCL.
- * One process per GPU, at most 8 ranks on one NVLink domain. */
+ * One process per GPU, at most 8 ranks on one NVLink domain.
+ * A rank waits up to "peer_timeout_ms" (default 10 minutes; 0 = for ever, like a NCCL collective) for its
+ * peers' limbs.  If they do not arrive, that rank's result carries EXBLAS_B200_ST_PEERTIMEOUT, its value is
+ * NaN and exblas_b200_fetch / the synchronous entry points return EXBLAS_B200_EPEER.  The ranks then no longer
+ * agree on which reductions have completed: results are undefined until every rank has called peer_export
+ * and peer_attach again. */
 int exblas_b200_peer_export(exblas_b200_handle_t handle, void* handle64);
 int exblas_b200_peer_attach(exblas_b200_handle_t handle, int nranks, int rank, const void* handles);
 
@@ -180,6 +193,17 @@ int exblas_b200_peer_attach(exblas_b200_handle_t handle, int nranks, int rank, c
 int exblas_b200_last_status(exblas_b200_handle_t handle, uint32_t* status_flags);
 const char* exblas_b200_last_error(exblas_b200_handle_t handle);
 const char* exblas_b200_strerror(int code);
+/* With option "phase_timing" = 1: copies the globaltimer stamps (ns) of the last reduction kernel, 16 per CTA
+ * (0 kernel start, 1 unrolled body done, 2..4 remainder / scalar part / flush, 5 block merge, 6 global merge,
+ * 7 normalised, 8 peers merged, 9 published), into out[capacity]; returns the number of CTAs written. */
+int64_t exblas_b200_phase_times(exblas_b200_handle_t handle, uint64_t* out, int64_t capacity);
+/* Measured ceilings for the roofline, on this GPU at this moment (diagnostics; what bench.py divides by):
+ * what = 0: FP64 pipe, DADD lane-instructions per second (d_buf / n unused);
+ * what = 1: HBM read-only stream in GB/s over the DEVICE buffer d_buf[0, n) (32-byte aligned), read with the
+ *           reduction kernels' own 256-bit L1-bypassing loads. */
+int exblas_b200_microbench(exblas_b200_handle_t handle, int what, const double* d_buf, int64_t n, double* result);
+/* Template instance and launch shape of the reduction kernel this handle launched last. */
+const char* exblas_b200_last_kernel(exblas_b200_handle_t handle);
 /* Kernels launched by this handle since creation (bench.py reports it as gpu_launches). */
 int64_t exblas_b200_launch_count(exblas_b200_handle_t handle);
 int exblas_b200_version(void);

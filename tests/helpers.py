@@ -75,7 +75,7 @@ def ref_round_model(limbs, fwords=20):
 
 
 def same_double(x, y):
-    """bit equality, with NaN == NaN"""
+    """bit equality (+0.0 and -0.0 differ), with NaN == NaN"""
     if isinstance(x, float) and isinstance(y, float) and math.isnan(x) and math.isnan(y):
         return True
-    return np.float64(x).view(np.uint64) == np.float64(y).view(np.uint64) or (x == 0 and y == 0)
+    return bool(np.float64(x).view(np.uint64) == np.float64(y).view(np.uint64))

@@ -50,6 +50,14 @@ def _worker(rank, world, port, n, q):
             v0 = xd.value_from(merged, st, 0)
             v1 = xd.value_from(merged, st, 1)
             out.append((kind, merged.tolist(), st, v0, v1))
+        # a multi-rank reducer without a transport must refuse to reduce (it would return this rank's shard only)
+        from exblas_b200._lib import ExblasB200Error
+        red = xd.DistributedReducer(None)
+        try:
+            red.exsum_async(4, None)
+            out.append(("no_transport", "did not raise"))
+        except ExblasB200Error:
+            out.append(("no_transport", "raised"))
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -79,7 +87,11 @@ def test_gloo_limb_allreduce(world, oracle):
         "illcond": cm.init_ill_cond(n, 1e32, seed=3),
         "cancel": cm.cancelling_pair(n, "sum"),
     }
-    for kind, merged, st, v0, v1 in results[0]:
+    for rec in results[0]:
+        if rec[0] == "no_transport":
+            assert rec[1] == "raised"
+            continue
+        kind, merged, st, v0, v1 = rec
         if kind == "nan":
             assert st == 1 and np.isnan(v0) and np.isnan(v1)
             continue

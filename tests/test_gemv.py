@@ -182,7 +182,8 @@ def test_exgemv_n_window_kernel(gpu, oracle):
                     for window, nshape in ((1, 0), (1, 1), (1, 2), (0, 0)):
                         gpu.set_option("window", window)
                         gpu.set_option("gemv_n_shape", nshape)
-                        for fpe in (0, 1):
+                        # fpe >= 2 with alpha == 1 takes the window kernel too; window = 0 keeps the expansion kernels covered
+                        for fpe in ((0, 1, 3, 8) if window else (0, 1, 2, 4, 8)):
                             for rm, want in ((0, w0), (1, w1)):
                                 dy = torch.from_numpy(y[:m].copy()).cuda()
                                 xb.exgemv("N", m, n, 1.0, da, lda, 0, dx, 1, 0, beta, dy, 1, 0, fpe, False, round_mode=rm, handle=gpu)

@@ -174,8 +174,50 @@ def test_result_independent_of_launch_shape(gpu, oracle):
                     v, l = gpu.exsum(n, d, 1, 0, fpe, ee, want_limbs=True)
                     assert same_double(v, v0) and (l == l0).all(), (T, blocks, fpe, ee)
     finally:
-        gpu.set_option("block_threads", 512)
-        gpu.set_option("blocks", 0)
+        gpu.set_option("auto_shape", 1)
+
+
+def test_small_and_mid_sizes_every_shape_regime(gpu, oracle):
+    """The size-dependent launch shapes (one CTA published from shared memory, 256-thread CTAs, equal tiles +
+    evenly spread remainder) around each of their thresholds, ExSUM and ExDOT, positive and signed data."""
+    nmax = (1 << 22) + 4099
+    a = cm.init_fpuniform(nmax, 664, 332, seed=21, neg_ratio=2)
+    b = cm.init_ill_cond(nmax, 1e32, seed=22)
+    da, db = dev(a), dev(b)
+    sizes = [1, 5, 511, 2048, 4096, 8191, 8192, 8193, 8197, 1 << 14, (1 << 16) + 1, 148 * 1024 * 4, 148 * 1024 * 4 + 5,
+             (1 << 20) - 3, 1 << 21, (1 << 22) - 1, 1 << 22, (1 << 22) + 1, nmax]
+    for n in sizes:
+        v0, l0 = oracle.exsum(a[:n], fpe=0)
+        d0, dl0 = oracle.exdot(a[:n], b[:n], fpe=0)
+        for fpe, ee in [(0, False), (3, False), (8, True)]:
+            v, l = gpu.exsum(n, da, 1, 0, fpe, ee, want_limbs=True)
+            assert same_double(v, v0) and (l == l0).all(), ("sum", n, fpe, ee)
+            v, l = gpu.exdot(n, da, 1, 0, db, 1, 0, fpe, ee, want_limbs=True)
+            assert same_double(v, d0) and (l == dl0).all(), ("dot", n, fpe, ee)
+        # misaligned start: alignment head + vector region + tail
+        v, l = gpu.exsum(n - 1, da, 1, 1, 4, False, want_limbs=True) if n > 1 else (0.0, None)
+        if n > 1:
+            w, wl = oracle.exsum(a[1:n], fpe=0)
+            assert same_double(v, w) and (l == wl).all(), ("sum+1", n)
+
+
+def test_partial_sums_near_the_top_of_the_layout(gpu):
+    """Inputs below 2^988 whose partial sums inside one expansion exceed it: every fpe must give the exact sum
+    (the expansion flush adds such a partial sum to limb 38 as an integer)."""
+    from fractions import Fraction
+    from helpers import limbs_from_fraction
+    for n, sign_every in [(1024, 0), (1024, 3), (300, 0), (4096 + 64, 2)]:
+        k = np.arange(n, dtype=np.float64)
+        a = (2.0 ** 987) * (1.0 + k * 2.0 ** -30)
+        if sign_every:
+            a[::sign_every] *= -1.0
+        exact = sum((Fraction(float(x)) for x in a), Fraction(0))
+        want = limbs_from_fraction(exact)
+        d = dev(a)
+        for fpe, ee in [(0, False), (2, False), (4, False), (8, False), (4, True), (8, True)]:
+            gpu.exsum_async(n, d, 1, 0, fpe, ee, 1)
+            v, l, st = gpu.fetch()
+            assert st == 0 and (l == want).all() and v == float(exact), (n, sign_every, fpe, ee, st)
 
 
 def test_permutation_invariance_and_rerun(gpu):
