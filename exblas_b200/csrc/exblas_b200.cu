@@ -41,8 +41,11 @@ constexpr int vectors_in_flight(int f, bool ee, bool dot) {
 #ifdef EXB_USUM
     return dot ? EXB_UDOT : EXB_USUM;
 #else
-    if (dot) return f <= 4 ? 4 : 3;
-    return f <= 4 ? 8 : 6;
+    // round 2, sustained (1 s, power-cap clocks) A/B at n = 2^30 (profiles/ab_sustained_r02.jsonl): six vectors per
+    // thread beat eight by 2-3 % on every ExSUM variant (fewer live registers, same bytes in flight per SM as the
+    // latency needs), four beat three by 6 % for the large ExDOT expansions; four vectors lose 2-4 %.
+    (void)f;
+    return dot ? 4 : 6;
 #endif
 }
 

@@ -911,6 +911,33 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
         // clear the (thread-private: no barrier needed) column while the first loads are in flight
         for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
         int bypass = 0, backoff = kBypassTiles;
+        // The first probe of the expansion is skipped when the exponents of the first tile alone span more than an
+        // F-level expansion can hold (log-uniform 2^+-332 against 53 F bits): walking a thrashing tile costs ~10 direct
+        // tiles, which vectors of 2^22..2^26 elements never amortise.  Later probes (after a bypass period) are real.
+        if (F > 0 && prm.adaptive) {
+            unsigned emax = 0u, emin = 0xfffu;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double xs[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                const double ys[4] = {vb[DOT ? u : 0].x, vb[DOT ? u : 0].y, vb[DOT ? u : 0].z, vb[DOT ? u : 0].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    unsigned e = ((unsigned)__double2hiint(xs[k]) >> 20) & 0x7ffu;
+                    if (DOT) {
+                        const unsigned eb = ((unsigned)__double2hiint(ys[k]) >> 20) & 0x7ffu;
+                        e = (e && eb) ? e + eb : 0u;                 // exponent of the product (+ 1023), 0 for zeros
+                    }
+                    emax = max(emax, e);
+                    emin = min(emin, e ? e : 0xfffu);
+                }
+            }
+            emax = __reduce_max_sync(kFullWarp, emax);
+            emin = __reduce_min_sync(kFullWarp, emin);
+            if (emax > emin && emax - emin > 53u * F + 64u) {
+                bypass = backoff;
+                backoff = min(backoff * 16, kBypassMax);
+            }
+        }
         for (unsigned it = 0; it < iters; ++it) {
             pa += tile_step;
             if (DOT) pb += tile_step;
@@ -1225,6 +1252,7 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, 
     w.emax = range_io[1];
     unsigned k = 0;
     int since_norm = 0;
+    bool abandoned = false;
     for (int bad = 0; k + DW <= iters && bad < 2; k += DW) {
         int missed = 0;
 #pragma unroll
@@ -1244,9 +1272,15 @@ __device__ __noinline__ unsigned reduce0_window_rows_wide_sum(const double* pa, 
             } else {
                 w = sumw_slow_group<W>(w, col, stride, a0, a1, a2, a3);
                 ++missed;
+                if (w.span == 0u) {          // what has missed cannot fit this window (warp-uniform): leave NOW, not a block later
+                    k += (unsigned)u + 1u;   // rows consumed so far, this one included
+                    abandoned = true;
+                    break;
+                }
             }
             if (loaded < iters) load_row(u);                    // row k + DW + u (after the slot has been consumed)
         }
+        if (abandoned) break;
         bad = (2 * missed > DW) ? bad + 1 : 0;
         if (w.span == 0u) bad = 2;
         if (w.cnt > (unsigned)(kWinFlushEvery - 4 * DW)) {
@@ -1287,36 +1321,14 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const __grid_co
         const long long row_step = (long long)gridDim.x * ROW;
         const double* pa = prm.a + prm.head + (long long)blockIdx.x * ROW + (long long)tid * 4;  // my first row
         const double* pb = DOT ? prm.b + prm.head + (long long)blockIdx.x * ROW + (long long)tid * 4 : nullptr;
-        // ---------------- loop 1: register window (out of line) ----------------
         unsigned k = 0;                                        // rows consumed so far
-        // (vectors too short for the windows to pay -- fewer than 32 rows per CTA, n < ~2^23 -- go straight to loop 2)
-        if constexpr (DW > 0) if (prm.window && iters >= 32u) {
-            for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
-            zeroed = true;
-            unsigned st1 = 0;
-            int range[2] = {4096, -4096};                      // exponents that have missed so far, warp-uniform
-            if constexpr (DOT) {
-                if (prm.window != 3)
-                    k = reduce0_window_rows_wide<DW, 3>(pa, pb, row_step, iters, col, stride, &st1, range);
-                if (k < iters && prm.window > 1)
-                    // (two rows in flight, refilled BEFORE the row is consumed: measured best of 2 / 3 / 4 rows, early / late
-                    // refill: 6.7 against 5.0-6.4 TB/s on ill-conditioned data; the wide loop spends ~45 instructions per product)
-                    k += reduce0_window_rows_wide<DW, 5, true>(pa + (long long)k * row_step, pb + (long long)k * row_step, row_step,
-                                                               iters - k, col, stride, &st1, range);
-            } else {
-                if (prm.window != 3)
-                    k = reduce0_window_rows_wide_sum<DW, 2>(pa, row_step, iters, col, stride, &st1, range);
-                if (k < iters && prm.window > 1)
-                    k += reduce0_window_rows_wide_sum<DW + 2, 3>(pa + (long long)k * row_step, row_step, iters - k, col, stride, &st1, range);
-            }
-            status |= st1;
-            pa += (long long)k * row_step;
-            if (DOT) pb += (long long)k * row_step;
-        }
-        // ---------------- loop 2: direct deposits, DD rows in flight; slot u holds row k + u ----------------
+        // The first DD rows are loaded at once (slot u holds row k + u), the column is cleared behind those loads, and
+        // the exponents of those rows decide -- for free, they are in registers -- whether the register windows are
+        // worth trying at all: data wider than the widest window (log-uniform 2^+-332) goes straight to the direct
+        // loop without paying for a window attempt (which cost ~5 us per launch before this check).
         Vec4 va[DD];
         Vec4 vb[DOT ? DD : 1];
-        unsigned loaded = k;                                   // rows loaded (or consumed by loop 1) so far
+        unsigned loaded = 0;                                   // rows loaded (or consumed by loop 1) so far
         auto load_row = [&](int u) {
             va[u] = ldg256(pa);
             if (DOT) vb[DOT ? u : 0] = ldg256(pb);
@@ -1328,10 +1340,67 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const __grid_co
 #pragma unroll
         for (int u = 0; u < DD; ++u)
             if (loaded < iters) load_row(u);
-        if (!zeroed) {
-            for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
-            zeroed = true;
+        for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+        zeroed = true;
+        // ---------------- loop 1: register window (out of line) ----------------
+        // (vectors too short for the windows to pay -- fewer than 32 rows per CTA, n < ~2^23 -- go straight to loop 2)
+        if constexpr (DW > 0) if (prm.window && iters >= 32u) {
+            unsigned emax = 0u, emin = 0xfffu;
+#pragma unroll
+            for (int u = 0; u < DD; ++u) {
+                const double xs[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                const double ys[4] = {vb[DOT ? u : 0].x, vb[DOT ? u : 0].y, vb[DOT ? u : 0].z, vb[DOT ? u : 0].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    unsigned e = ((unsigned)__double2hiint(xs[q]) >> 20) & 0x7ffu;
+                    if (DOT) {
+                        const unsigned eb = ((unsigned)__double2hiint(ys[q]) >> 20) & 0x7ffu;
+                        e = (e && eb) ? e + eb : 0u;           // exponent of the product (+ 1023), 0 for zeros
+                    }
+                    emax = max(emax, e);
+                    emin = min(emin, e ? e : 0xfffu);
+                }
+            }
+            emax = __reduce_max_sync(kFullWarp, emax);
+            emin = __reduce_min_sync(kFullWarp, emin);
+            constexpr unsigned kWidest = DOT ? 50u + 52u * 2u : 51u + 52u;      // W = 5 products / W = 3 summands
+            if (!(emax > emin && emax - emin + 1u > kWidest)) {
+                const double* pa0 = pa - (long long)loaded * row_step;           // back to my first row
+                const double* pb0 = DOT ? pb - (long long)loaded * row_step : nullptr;
+                unsigned st1 = 0;
+                int range[2] = {4096, -4096};                  // exponents that have missed so far, warp-uniform
+                if constexpr (DOT) {
+                    if (prm.window != 3)
+                        k = reduce0_window_rows_wide<DW, 3>(pa0, pb0, row_step, iters, col, stride, &st1, range);
+                    if (k < iters && prm.window > 1)
+                        // (two rows in flight, refilled BEFORE the row is consumed: measured best of 2 / 3 / 4 rows, early / late
+                        // refill: 6.7 against 5.0-6.4 TB/s on ill-conditioned data; the wide loop spends ~45 instructions per product)
+                        k += reduce0_window_rows_wide<DW, 5, true>(pa0 + (long long)k * row_step, pb0 + (long long)k * row_step, row_step,
+                                                                   iters - k, col, stride, &st1, range);
+                } else {
+                    if (prm.window != 3)
+                        k = reduce0_window_rows_wide_sum<DW, 2>(pa0, row_step, iters, col, stride, &st1, range);
+                    if (k < iters && prm.window > 1)
+                        k += reduce0_window_rows_wide_sum<DW + 2, 3>(pa0 + (long long)k * row_step, row_step, iters - k, col, stride, &st1, range);
+                }
+                status |= st1;
+                // ---------------- loop 2 restarts at row k (rows that were in flight come from L2 now) ----------------
+                pa = pa0 + (long long)k * row_step;
+                if (DOT) pb = pb0 + (long long)k * row_step;
+                loaded = k;
+#pragma unroll
+                for (int u = 0; u < DD; ++u) {
+                    // (every slot is redefined here, so that none of the first prefetch stays live across the calls above)
+                    if (loaded < iters) {
+                        load_row(u);
+                    } else {
+                        va[u] = Vec4{0.0, 0.0, 0.0, 0.0};
+                        if (DOT) vb[DOT ? u : 0] = Vec4{0.0, 0.0, 0.0, 0.0};
+                    }
+                }
+            }
         }
+        // ---------------- loop 2: direct deposits, DD rows in flight; slot u holds row k + u ----------------
         auto consume = [&](int u, bool all_pos) {
             if (DOT) {
                 const double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};

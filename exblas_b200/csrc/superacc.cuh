@@ -310,6 +310,41 @@ EXB_D void sts64(unsigned addr, unsigned long long v) {
 // = D1 and bits(rem + 1.5) - bits(1.5) = rem * 2^52, which keeps the integer pipe (the busier
 // one here) to ~15 instructions per element.  The sign of x is applied to D0 by flipping rem's
 // sign bit and to D1 by a two's-complement negate folded into the 3-input accumulate add.
+#ifdef EXB_INT_SPLIT
+// Integer-only variant of the split (experiment, profiles/README.md "deposit split"): x = m * 2^(E-1075) with the
+// 53-bit mantissa m; in units of the accumulator LSB (2^-1040) that is m << p, p = E - 35.  With J0 = p / 52 and
+// s = p % 52 the two digits are D0 = (m << s) mod 2^52 (limb J0) and D1 = m >> (52 - s) (limb J0 + 1 = J1), both
+// non-negative: eleven shift / logic instructions and no FP64-pipe work at all.
+EXB_D void split_int(unsigned lo, unsigned ahi, unsigned& J1, unsigned long long& d0, unsigned long long& d1) {
+    const unsigned E = ahi >> 20;
+    J1 = __umulhi(E + 17u, 82595525u);                            // floor((E+17)/52) = J0 + 1, in [1, 38]
+    const unsigned s = (E + 17u) - J1 * 52u;                      // (E - 35) mod 52
+    const unsigned long long m = ((unsigned long long)((ahi & 0xfffffu) | 0x100000u) << 32) | lo;
+    d0 = (m << s) & (unsigned long long)kLimbMask;
+    d1 = m >> (52u - s);
+}
+EXB_D void deposit_fast(unsigned col, unsigned stride, unsigned lo, unsigned hi) {
+    unsigned J1;
+    unsigned long long d0, d1;
+    split_int(lo, hi & 0x7fffffffu, J1, d0, d1);
+    const unsigned long long sm = (unsigned long long)((long long)(int)hi >> 31);   // all ones when x < 0
+    const unsigned a1 = col + J1 * stride;
+    const unsigned a0 = (col - stride) + J1 * stride;
+    const unsigned long long v0 = lds64(a0), v1 = lds64(a1);
+    sts64(a0, v0 + (d0 ^ sm) - sm);
+    sts64(a1, v1 + (d1 ^ sm) - sm);
+}
+EXB_D void deposit_fast_pos(unsigned col, unsigned stride, unsigned lo, unsigned hi) {
+    unsigned J1;
+    unsigned long long d0, d1;
+    split_int(lo, hi, J1, d0, d1);
+    const unsigned a1 = col + J1 * stride;
+    const unsigned a0 = (col - stride) + J1 * stride;
+    const unsigned long long v0 = lds64(a0), v1 = lds64(a1);
+    sts64(a0, v0 + d0);
+    sts64(a1, v1 + d1);
+}
+#else
 EXB_D void deposit_fast(unsigned col, unsigned stride, unsigned lo, unsigned hi) {
     const unsigned ahi = hi & 0x7fffffffu;
     const unsigned E = ahi >> 20;
@@ -352,6 +387,7 @@ EXB_D void deposit_fast_pos(unsigned col, unsigned stride, unsigned lo, unsigned
     sts64(a0, v0 + d0);
     sts64(a1, v1 + d1);
 }
+#endif  // EXB_INT_SPLIT
 
 // distance of |x| above the lower edge of the fast range, as an unsigned 32-bit key on the high
 // word (so that one unsigned compare tests both edges, and a max over several keys tests them all)
