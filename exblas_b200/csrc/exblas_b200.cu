@@ -15,10 +15,17 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cctype>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_set>
+#include <vector>
+
+#include <sched.h>
 
 #include "../../include/exblas_b200.h"
 #include "reduce_kernel.cuh"
@@ -91,6 +98,119 @@ constexpr int kNcclSum = 0;     // ncclSum
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+// Host copy pool: PAGEABLE host input (what the reference's callers pass: new[] / _mm_malloc, tests/test.exsum.cpu.cpp:79,
+// src/gpu/blas/blas1/ExSUM.cpp:126) cannot be read by the GPU's copy engines directly; the driver's own staging of a
+// pageable cudaMemcpy runs at ~11 GB/s.  Here a few worker threads copy each chunk into pinned bounce buffers in
+// parallel while the previous chunk is in flight over PCIe, which brings the pageable path to several times that.
+// Workers are pinned to the CPUs local to the GPU (sysfs local_cpulist) when the process is allowed to run there.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+class CopyPool {
+public:
+    CopyPool(int nthreads, const std::vector<int>& cpus) : n_(nthreads < 1 ? 1 : nthreads) {
+        for (int i = 1; i < n_; ++i) workers_.emplace_back([this, i, cpus] { run(i, cpus); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    int threads() const { return n_; }
+    // blocking parallel memcpy of up to two segments (the calling thread takes part as worker 0)
+    void copy(void* d0, const void* s0, size_t b0, void* d1 = nullptr, const void* s1 = nullptr, size_t b1 = 0) {
+        seg_[0] = {(char*)d0, (const char*)s0, b0};
+        seg_[1] = {(char*)d1, (const char*)s1, b1};
+        if (n_ == 1 || b0 + b1 < (size_t)1 << 20) {
+            work(0, 1);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            pending_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        work(0, n_);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    struct Seg { char* d; const char* s; size_t b; };
+    void work(int i, int n) {
+        for (const Seg& g : seg_) {
+            if (!g.b) continue;
+            const size_t per = ((g.b + n - 1) / n + 4095) & ~(size_t)4095;
+            const size_t lo = (size_t)i * per, hi = lo + per < g.b ? lo + per : g.b;
+            if (lo < hi) memcpy(g.d + lo, g.s + lo, hi - lo);
+        }
+    }
+    void run(int i, std::vector<int> cpus) {
+        if (!cpus.empty()) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            for (int c : cpus) if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &set);
+            sched_setaffinity(0, sizeof(set), &set);      // best effort: fails harmlessly outside the allowed cpuset
+        }
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            work(i, n_);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    unsigned long long gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+    Seg seg_[2] = {};
+};
+
+// CPUs local to a PCI device: /sys/bus/pci/devices/<domain:bus:dev.fn>/local_cpulist ("0-31,64-95")
+std::vector<int> local_cpus_of_device(int device) {
+    std::vector<int> cpus;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return cpus;
+    }
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return cpus;
+    char line[1024] = {0};
+    if (fgets(line, sizeof line, f)) {
+        for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            const int k = sscanf(tok, "%d-%d", &a, &b);
+            if (k == 1) b = a;
+            if (k >= 1)
+                for (int c = a; c <= b && cpus.size() < 4096; ++c) cpus.push_back(c);
+        }
+    }
+    fclose(f);
+    return cpus;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------------
 struct exblas_b200_handle_s {
@@ -110,6 +230,12 @@ struct exblas_b200_handle_s {
     int64_t opt_block_threads = kMaxT;
     int64_t opt_blocks = 0;
     int64_t opt_host_chunk = (int64_t)1 << 23;
+    int64_t opt_host_threads = 0;           // pageable host input: copy threads (0 = automatic, 1 = none: plain cudaMemcpy staging)
+    int64_t opt_pageable_chunk = (int64_t)1 << 21;   // elements per chunk through the pinned bounce buffers
+    CopyPool* pool = nullptr;
+    double* h_bounce[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // pinned [ring][a|b]
+    int64_t bounce_elems = 0;
+    cudaEvent_t bounce_free[3] = {nullptr, nullptr, nullptr};
     int64_t opt_adaptive = 1;
     int64_t opt_gemv_parts = 0;
     int64_t opt_gemv_t_shape = 2;
@@ -341,24 +467,79 @@ int reduce_from_host(exblas_b200_handle_t h, bool dot, int f, bool ee, const dou
     return rc;
 }
 
+bool is_pageable_host_pointer(const void* p) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// pinned bounce ring + copy threads for pageable input (allocated on first use)
+int ensure_bounce(exblas_b200_handle_t h, int64_t elems, bool dot) {
+    if (!h->pool) {
+        int nt = (int)h->opt_host_threads;
+        if (nt <= 0) {
+            const unsigned hw = std::thread::hardware_concurrency();
+            const int64_t ranks = h->opt_world_size > 1 ? h->opt_world_size : 1;
+            nt = (int)((hw ? hw : 8u) / (ranks > 1 ? ranks : 2));   // a multi-rank job shares the cores; alone, leave half to the caller
+            if (nt > 8) nt = 8;
+            if (nt < 2) nt = 2;
+        }
+        h->pool = new CopyPool(nt, local_cpus_of_device(h->device));
+    }
+    if (h->bounce_elems >= elems && (!dot || h->h_bounce[0][1])) return EXBLAS_B200_OK;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (h->h_bounce[i][j]) {
+                cudaFreeHost(h->h_bounce[i][j]);
+                h->h_bounce[i][j] = nullptr;
+            }
+    h->bounce_elems = 0;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < (dot ? 2 : 1); ++j) CK(cudaHostAlloc(&h->h_bounce[i][j], (size_t)elems * sizeof(double), cudaHostAllocDefault));
+        if (!h->bounce_free[i]) CK(cudaEventCreateWithFlags(&h->bounce_free[i], cudaEventDisableTiming));
+    }
+    h->bounce_elems = elems;
+    return EXBLAS_B200_OK;
+}
+
 int reduce_from_host_impl(exblas_b200_handle_t h, bool dot, int f, bool ee, const double* a, int64_t inca, const double* b,
                           int64_t incb, int64_t n, int round_mode) {
-    int64_t chunk = h->opt_host_chunk;
-    if (chunk > n) chunk = n;
     const int64_t max_inc = dot ? (inca > incb ? inca : incb) : inca;
+    // PAGEABLE input of some size: worker threads copy chunk k + 1 into a pinned bounce buffer while chunk k is on the bus
+    const bool bounce = h->opt_host_threads != 1 && n * max_inc >= ((int64_t)1 << 19) &&
+                        (is_pageable_host_pointer(a) || (dot && is_pageable_host_pointer(b)));
+    int64_t chunk = bounce ? h->opt_pageable_chunk : h->opt_host_chunk;
+    if (chunk > n) chunk = n;
     const int64_t span = (chunk - 1) * max_inc + 1;            // doubles copied per chunk and stream
     int rc = ensure_stage(h, span, dot);
     if (rc) return rc;
+    if (bounce) {
+        rc = ensure_bounce(h, span, dot);
+        if (rc) return rc;
+    }
     int k = 0;
     for (int64_t i0 = 0; i0 < n; i0 += chunk, ++k) {
         const int64_t cnt = (n - i0 < chunk) ? n - i0 : chunk;
         const int s = k & 1;
+        const size_t bytes_a = (size_t)((cnt - 1) * inca + 1) * sizeof(double);
+        const size_t bytes_b = dot ? (size_t)((cnt - 1) * incb + 1) * sizeof(double) : 0;
+        const double* src_a = a + i0 * inca;
+        const double* src_b = dot ? b + i0 * incb : nullptr;
+        if (bounce) {
+            const int r = k % 3;
+            if (k >= 3) CK(cudaEventSynchronize(h->bounce_free[r]));        // its previous H2D has left the buffer
+            h->pool->copy(h->h_bounce[r][0], src_a, bytes_a, dot ? h->h_bounce[r][1] : nullptr, src_b, bytes_b);
+            src_a = h->h_bounce[r][0];
+            src_b = h->h_bounce[r][1];
+        }
         if (k >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->consumed[s], 0));
-        CK(cudaMemcpyAsync(h->d_stage[s][0], a + i0 * inca, (size_t)((cnt - 1) * inca + 1) * sizeof(double),
-                           cudaMemcpyHostToDevice, h->copy_stream));
-        if (dot)
-            CK(cudaMemcpyAsync(h->d_stage[s][1], b + i0 * incb, (size_t)((cnt - 1) * incb + 1) * sizeof(double),
-                               cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaMemcpyAsync(h->d_stage[s][0], src_a, bytes_a, cudaMemcpyHostToDevice, h->copy_stream));
+        if (dot) CK(cudaMemcpyAsync(h->d_stage[s][1], src_b, bytes_b, cudaMemcpyHostToDevice, h->copy_stream));
+        if (bounce) CK(cudaEventRecord(h->bounce_free[k % 3], h->copy_stream));
         CK(cudaEventRecord(h->copied[s], h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, h->copied[s], 0));
         const int last = (i0 + cnt >= n);
@@ -766,6 +947,12 @@ int exblas_b200_destroy(exblas_b200_handle_t h) {
             if (h->d_stage[i][j]) cudaFree(h->d_stage[i][j]);
     for (int r = 0; r < h->peer_ranks; ++r)
         if (h->peer_box[r] && h->peer_box[r] != h->d_mailbox) cudaIpcCloseMemHandle(h->peer_box[r]);
+    delete h->pool;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 2; ++j)
+            if (h->h_bounce[i][j]) cudaFreeHost(h->h_bounce[i][j]);
+        if (h->bounce_free[i]) cudaEventDestroy(h->bounce_free[i]);
+    }
     if (h->d_mailbox) cudaFree(h->d_mailbox);
     if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
     if (h->d_phase) cudaFree(h->d_phase);
@@ -843,6 +1030,16 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "host_chunk_elems")) {
         if (value < 1024) return EXBLAS_B200_EINVAL;
         h->opt_host_chunk = value;
+    } else if (!strcmp(name, "pageable_chunk_elems")) {
+        if (value < 1024) return EXBLAS_B200_EINVAL;
+        h->opt_pageable_chunk = value;
+    } else if (!strcmp(name, "host_threads")) {
+        if (value < 0 || value > 64) return EXBLAS_B200_EINVAL;
+        if (h->pool && value != h->opt_host_threads) {
+            delete h->pool;
+            h->pool = nullptr;
+        }
+        h->opt_host_threads = value;
     } else {
         return EXBLAS_B200_EINVAL;
     }

@@ -10,8 +10,10 @@
  *
  * Plain pointers and sizes only.  Every data pointer may be a host pointer (pageable or pinned)
  * or a device / managed pointer on the handle's GPU; the library finds out with
- * cudaPointerGetAttributes.  Host inputs are streamed through device staging buffers in chunks
- * (the reference copies the whole vector on every call, ExSUM.cpp:126).
+ * cudaPointerGetAttributes.  Host inputs are streamed through device staging buffers in chunks,
+ * copy overlapped with the reduction (the reference copies the whole vector on every call,
+ * ExSUM.cpp:126); pageable memory -- what new[] / malloc / _mm_malloc return -- is first gathered into
+ * pinned bounce buffers by a few library threads, chunk k + 1 while chunk k is on the bus.
  *
  * Argument meaning follows the reference's GPU kernels (ExSUM.FPE.cl:252,298-299): `n` elements
  * a[offset + i*inca], i = 0..n-1.  fpe < 2 (exsum) / fpe < 3 (exdot) selects the
@@ -71,7 +73,9 @@ int exblas_b200_set_stream(exblas_b200_handle_t handle, void* stream);
 /* Tuning knobs (performance only, never the result): "block_threads" (multiple of 32, <= 512) and
  * "blocks" (0 = automatic) fix the launch shape by hand ("auto_shape" = 1 returns to the size-dependent
  * one: a single CTA up to "solo_max_elems" elements, 256-thread CTAs up to "small_max_elems", else one
- * 512-thread CTA per SM), "host_chunk_elems", "host_threads", "gemv_parts" (0 = automatic column split, <= 1024),
+ * 512-thread CTA per SM), "host_chunk_elems" (elements per H2D chunk of pinned host input), "host_threads" /
+ * "pageable_chunk_elems" (pageable host input goes through pinned bounce buffers filled by that many copy
+ * threads, 0 = automatic, 1 = none: the driver's own pageable staging), "gemv_parts" (0 = automatic column split, <= 1024),
  * "adaptive" (1 = a warp bypasses the expansion and deposits straight into its superaccumulators while
  * the expansion overflows on most elements; 0 = always walk all fpe levels, as the reference kernels do),
  * "window" (register window of the superaccumulator-only kernels: 0 off, 1 narrow windows, 2 narrow then

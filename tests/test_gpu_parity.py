@@ -155,8 +155,26 @@ def test_host_streaming_chunks(gpu, oracle):
             v, l = gpu.exsum(n // 3, a, 3, 1, 0, False, want_limbs=True)
             w, wl = oracle.exsum(a, inca=3, offset=1, n=n // 3, fpe=0)
             assert same_double(v, w) and (l == wl).all(), chunk
+        # pageable memory (numpy) takes the pinned bounce ring filled by the copy threads; pinned memory and
+        # host_threads = 1 (the driver's own pageable staging) take the direct H2D path: all three must agree
+        import torch
+        pin_a = torch.from_numpy(a).pin_memory()
+        pin_b = torch.from_numpy(b).pin_memory()
+        for threads, pchunk in ((0, 1 << 21), (3, 7001), (8, 65536), (1, 1 << 21)):
+            gpu.set_option("host_threads", threads)
+            gpu.set_option("pageable_chunk_elems", pchunk)
+            for src_a, src_b in ((a, b), (pin_a, pin_b)):
+                v, l = gpu.exsum(n, src_a, 1, 0, 3, False, want_limbs=True)
+                assert same_double(v, v0) and (l == l0).all(), (threads, pchunk)
+                v, l = gpu.exdot(n, src_a, 1, 0, src_b, 1, 0, 0, False, want_limbs=True)
+                assert same_double(v, d0) and (l == dl0).all(), (threads, pchunk)
+            v, l = gpu.exsum(n // 3, a, 3, 1, 8, True, want_limbs=True)
+            w, wl = oracle.exsum(a, inca=3, offset=1, n=n // 3, fpe=0)
+            assert same_double(v, w) and (l == wl).all(), (threads, pchunk)
     finally:
         gpu.set_option("host_chunk_elems", 1 << 23)
+        gpu.set_option("host_threads", 0)
+        gpu.set_option("pageable_chunk_elems", 1 << 21)
 
 
 def test_result_independent_of_launch_shape(gpu, oracle):
