@@ -4,7 +4,8 @@
            early_exit=False) -> 0,  y overwritten with alpha*A*x + beta*y, every element the rounded
                                     exact value
 
-transa == 'N' is the tuned case (BASELINE config 5); 'T' is correct but not yet tuned.  a, x, y: numpy float64 arrays (host, y is
+transa == 'N' (BASELINE config 5: thread per row) and 'T' (warp per output) both run register-window kernels for
+alpha == 1 and the general expansion kernel otherwise.  a, x, y: numpy float64 arrays (host, y is
 updated in place) or torch CUDA float64 tensors (device pointers, asynchronous on the handle's
 stream; the wrapper synchronises before returning, like the reference).
 """

@@ -240,6 +240,7 @@ struct exblas_b200_handle_s {
     int64_t opt_gemv_parts = 0;
     int64_t opt_gemv_t_shape = 2;
     int64_t opt_gemv_n_shape = 1;
+    int64_t opt_gemv_prefetch = 2;          // ExGEMV window kernels: L2 bulk-prefetch distance in rounds (0 = off)
     int64_t opt_window = 2;                 // register window in the superaccumulator-only kernels (performance only)
     bool opt_shape_fixed = false;           // "block_threads" / "blocks" were set by hand: no size-dependent launch shape
     int64_t opt_solo_max = (int64_t)1 << 13;    // vectors up to this length: one CTA, published from shared memory
@@ -677,6 +678,7 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
         p.beta = beta;
         p.ws = h->d_ws;
         p.round_mode = round_mode;
+        p.l2_prefetch = (((uintptr_t)a % 16) == 0 && (rs % 2) == 0) ? (int)h->opt_gemv_prefetch : 0;
         // launch shapes (option "gemv_t_shape"): threads x groups of 4 rows in flight per lane x rows of x per buffer
         struct TShape { int T, chunk; gemv_fn fn; };
         static const TShape shapes[] = {
@@ -753,6 +755,7 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     p.round_mode = round_mode;
     p.adaptive = h->opt_adaptive ? 1 : 0;
     p.x_vec_ok = (incx == 1 && ((uintptr_t)x % 32) == 0) ? 1 : 0;       // part starts are multiples of 4 columns
+    p.l2_prefetch = (windowed && ((uintptr_t)a % 16) == 0 && (cs % 2) == 0 && (T % 2) == 0) ? (int)h->opt_gemv_prefetch : 0;
     gemv_fn fn = windowed ? nsh.fn : (alpha == 1.0 ? select_gemv<true>(f, ee) : select_gemv<false>(f, ee));
     const size_t smem = windowed ? (size_t)Tmax * kLimbs * sizeof(long long) + (size_t)cpp * sizeof(double)   // fixed limb stride
                                  : (size_t)T * kLimbs * sizeof(long long);
@@ -1019,6 +1022,9 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "gemv_t_shape")) {
         if (value < 0 || value > 3) return EXBLAS_B200_EINVAL;
         h->opt_gemv_t_shape = value;
+    } else if (!strcmp(name, "gemv_prefetch")) {
+        if (value < 0 || value > 16) return EXBLAS_B200_EINVAL;
+        h->opt_gemv_prefetch = value;
     } else if (!strcmp(name, "gemv_n_shape")) {
         if (value < 0 || value > 2) return EXBLAS_B200_EINVAL;
         h->opt_gemv_n_shape = value;

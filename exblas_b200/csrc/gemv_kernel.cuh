@@ -1,6 +1,7 @@
 // gemv_kernel.cuh -- ExGEMV (y := alpha*op(A)*x + beta*y, column-major A) for sm_100a.
-// 'N' is the tuned case (coalesced); 'T' runs the same kernel with the strides swapped (correct,
-// uncoalesced: SURVEY section 8f rank 3 leaves its fast path for later).
+// 'N' (thread per row, coalesced column loads) and 'T' (warp per output, coalesced column streaming) each have a
+// register-window kernel for alpha == 1 (every fpe value) and share exgemv_n_kernel -- expansions, any alpha, any
+// strides -- as the general path.
 //
 // SURVEY.md section 8f rank 1 / BASELINE config 5.  Replaces the reference's OpenCL kernels
 //   gemv / gemv_reduce   src/gpu/blas/blas2/ExGEMV.FPE.cl:199-379, 561-580, ExGEMV.FPE.EX.{4,6,8}.cl,
@@ -39,12 +40,40 @@ struct GemvParams {
     int round_mode;
     int adaptive;
     int x_vec_ok;           // x contiguous and 32-byte aligned at every part start
+    int l2_prefetch;        // window kernels: bulk L2 prefetch distance in rounds (0 = off; needs A 16-byte aligned, lda even)
 };
+
+// TMA-engine prefetch of a contiguous run of global memory into L2 (no destination in shared memory, no completion to
+// wait for): SASS UBLKPF.  `bytes` must be a multiple of 16 and `p` 16-byte aligned.
+EXB_D void bulk_prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 EXB_D Vec4 ldg256_cached(const double* p) {     // through L1: x is re-read by every warp of the CTA
     Vec4 r;
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
+}
+
+
+// alpha * a = p + e exactly (TwoProductFMA) -- provided nothing underflows or overflows on the way.  The exact range is
+// 2^-959 <= |alpha * a| < 2^1024; outside it (and for non-zero operands) the scaled value cannot be represented by two
+// doubles, so it is dropped and FLAGGED instead of being summed inexactly: kStTooSmall (bits were lost: the row sum is
+// no longer exact) / kStTooLarge.  Inf / NaN operands pass through with their IEEE meaning.
+EXB_D void scale_exact(double alpha, double a, double& p, double& e, unsigned& status) {
+    p = __dmul_rn(alpha, a);
+    e = __fma_rn(alpha, a, -p);
+    const unsigned ph = (unsigned)__double2hiint(p) & 0x7fffffffu;
+    if (ph - (64u << 20) >= ((0x7ffu - 64u) << 20)) {                     // |p| < 2^-959, or Inf / NaN
+        const unsigned ah = (unsigned)__double2hiint(alpha) & 0x7fffffffu, xh = (unsigned)__double2hiint(a) & 0x7fffffffu;
+        const bool finite = ah < 0x7ff00000u && xh < 0x7ff00000u;
+        const bool nonzero = ((ah | (unsigned)__double2loint(alpha)) != 0u) && ((xh | (unsigned)__double2loint(a)) != 0u);
+        if (finite && nonzero) {
+            status |= ph >= 0x7ff00000u ? kStTooLarge : kStTooSmall;
+            p = 0.0;
+        }
+        if (finite) e = 0.0;                                              // (e of an exact zero / a dropped value)
+    }
 }
 
 template <int F, bool EE, bool ALPHA1, int U, int MAXT>
@@ -126,10 +155,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
             // alpha * a = p1 + e1 exactly; then p1 * x and e1 * x
             double p1[4], e1[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                p1[k] = __dmul_rn(prm.alpha, xa[k]);
-                e1[k] = __fma_rn(prm.alpha, xa[k], -p1[k]);
-            }
+            for (int k = 0; k < 4; ++k) scale_exact(prm.alpha, xa[k], p1[k], e1[k], status);
             if (direct) {
                 double none[1][expansions(0)];
                 mul_add4<0, false, true>(col, stride, none, status, p1, xb);
@@ -187,8 +213,8 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
         if constexpr (unit_alpha) {
             mul_add1<F, EE>(col, stride, a, status, av, xv);
         } else {
-            const double p1 = __dmul_rn(prm.alpha, av);
-            const double e1 = __fma_rn(prm.alpha, av, -p1);
+            double p1, e1;
+            scale_exact(prm.alpha, av, p1, e1, status);
             mul_add1<F, EE>(col, stride, a, status, p1, xv);
             mul_add1<F, EE>(col, stride, a, status, e1, xv);
         }
@@ -282,9 +308,23 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
     int since_norm = 0;
     int r = 0;
     // ---- loop 1: register window.  Two rounds in a row that mostly miss (wide-range rows) end it. ----
+    // L2 prefetch (TMA engine, UBLKPF): the kernel is bound by the latency of its 8-byte global loads (ncu, round 1: a
+    // quarter of all stall samples on the first use of a loaded value; 64 KB in flight per SM is all the registers
+    // allow).  Every round, warp w asks for column 4 U (r + D) + w of this CTA's row block -- one contiguous run of
+    // T * 8 bytes -- so that D rounds later the loads hit L2 instead of DRAM.
+    const long long rows_here = prm.m - (long long)blockIdx.x * T < (long long)T ? prm.m - (long long)blockIdx.x * T : (long long)T;
+    int pf_cidx = prm.l2_prefetch * 4 * U + (int)(tid >> 5);                      // this warp's column (of the part) to ask for next
+    const double* pf_ptr = prm.a + (long long)blockIdx.x * T * prm.rs + cs * (c0 + pf_cidx);
+    const unsigned pf_bytes = (prm.l2_prefetch > 0 && (tid & 31u) == 0u && (tid >> 5) < 4u * U) ? ((unsigned)(rows_here * 8) & ~15u) : 0u;
+    auto prefetch_round = [&]() {
+        if (pf_bytes && pf_cidx < ncols) bulk_prefetch_l2(pf_ptr, pf_bytes);
+        pf_ptr += astep * U;
+        pf_cidx += 4 * U;
+    };
     for (int bad = 0; r < rounds && bad < 2; ++r) {
         const bool has_next = r + 1 < rounds;
         int missed = 0;
+        prefetch_round();
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
@@ -328,6 +368,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
         unsigned status = w.st;
         for (; r < rounds; ++r) {
             const bool has_next = r + 1 < rounds;
+            prefetch_round();
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
@@ -408,8 +449,8 @@ __device__ __noinline__ void gemv_t_store(const long long* wl, unsigned st, doub
         if (beta == 1.0) {
             st |= accumulate_double(acc, yv);
         } else {
-            const double p = __dmul_rn(beta, yv);
-            const double e = __fma_rn(beta, yv, -p);
+            double p, e;
+            scale_exact(beta, yv, p, e, st);
             st |= accumulate_double(acc, p);
             if (!(e != e)) st |= accumulate_double(acc, e);
         }
@@ -485,6 +526,12 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (rounds > 0) load_group(u);
+        // L2 prefetch (TMA engine, UBLKPF): lane 0 asks for the 128 U rows of this warp's column that round r + D will read
+        const double* pf_col = prm.a + j * prm.rs;
+        const int pf_dist = prm.l2_prefetch;
+        auto prefetch_round = [&](long long rr) {
+            if (pf_dist > 0 && lane == 0u && rr + pf_dist < rounds) bulk_prefetch_l2(pf_col + (rr + pf_dist) * (128 * U), 128u * U * 8u);
+        };
         __syncthreads();                                                             // previous set's readers of both x buffers are done
         stage(0);
         int since_norm = 0;
@@ -499,55 +546,55 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
             }
             return xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u) + (unsigned)(r % RPC) * (128u * U * 8u) + (VEC ? 32u : 8u) * lane;
         };
-        long long r = 0;
-        // ---- loop 1: register window; two rounds in a row that mostly miss end it (for this and the next 7 columns) ----
-        if (skip_window > 0) --skip_window;
-        else for (int bad = 0; r < rounds && bad < 2; ++r) {
+        // ONE loop over the rounds with ONE call site of chunk_gate (its __syncthreads must be reached by every warp from
+        // the same program point, whatever mode the warp is in).  Per warp: register-window mode until two rounds in a
+        // row mostly miss (then ordinary deposits for the rest of this column and the next 7 columns).
+        bool windowed = skip_window == 0;
+        if (!windowed) --skip_window;
+        int bad = 0;
+        for (long long r = 0; r < rounds; ++r) {
             unsigned xaddr = chunk_gate(r);
             const bool has_next = r + 1 < rounds;
-            int missed = 0;
+            prefetch_round(r);
+            if (windowed) {
+                int missed = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
-                if (has_next) load_group(u);
-                double x0, x1, x2, x3;
-                load_x(xaddr, x0, x1, x2, x3);
-                xaddr += 1024u;
-                const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
-                const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
-                const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
-                const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
-                const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
-                const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
-                if (__all_sync(0xffffffffu, mine)) {
-                    win_add_product(w, p0, __fma_rn(a0, x0, -p0));
-                    win_add_product(w, p1, __fma_rn(a1, x1, -p1));
-                    win_add_product(w, p2, __fma_rn(a2, x2, -p2));
-                    win_add_product(w, p3, __fma_rn(a3, x3, -p3));
-                    w.cnt += 4u;
-                } else {
-                    w = prod_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
-                    ++missed;
+                for (int u = 0; u < U; ++u) {
+                    const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
+                    if (has_next) load_group(u);
+                    double x0, x1, x2, x3;
+                    load_x(xaddr, x0, x1, x2, x3);
+                    xaddr += 1024u;
+                    const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
+                    const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
+                    const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
+                    const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
+                    const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
+                    const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+                    if (__all_sync(0xffffffffu, mine)) {
+                        win_add_product(w, p0, __fma_rn(a0, x0, -p0));
+                        win_add_product(w, p1, __fma_rn(a1, x1, -p1));
+                        win_add_product(w, p2, __fma_rn(a2, x2, -p2));
+                        win_add_product(w, p3, __fma_rn(a3, x3, -p3));
+                        w.cnt += 4u;
+                    } else {
+                        w = prod_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
+                        ++missed;
+                    }
                 }
-            }
-            bad = (2 * missed > U) ? bad + 1 : 0;
-            if (bad >= 2) skip_window = 7;
-            if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) {
-                w = win_flush_products(w, col, stride);
-                since_norm += 4;
-            }
-            since_norm += missed * 12;
-            if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
-                bound_column(col, stride);
-                since_norm = 0;
-            }
-        }
-        // ---- loop 2: wide-range column, every product takes the ordinary path, inlined ----
-        if (r < rounds) {
-            unsigned status = w.st;
-            for (; r < rounds; ++r) {
-                unsigned xaddr = chunk_gate(r);
-                const bool has_next = r + 1 < rounds;
+                bad = (2 * missed > U) ? bad + 1 : 0;
+                if (bad >= 2) {                                                      // warp-uniform (the votes are)
+                    skip_window = 7;
+                    windowed = false;
+                }
+                if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) {
+                    w = win_flush_products(w, col, stride);
+                    since_norm += 4;
+                }
+                since_norm += missed * 12;
+            } else {
+                // wide-range column: every product takes the ordinary path, inlined
+                unsigned status = w.st;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
@@ -558,13 +605,13 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
                     double none[1][expansions(0)];
                     mul_add4<0, false, true>(col, stride, none, status, xa, xb);
                 }
+                w.st = status;
                 since_norm += 8 * U;
-                if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
-                    bound_column(col, stride);
-                    since_norm = 0;
-                }
             }
-            w.st = status;
+            if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
+                bound_column(col, stride);
+                since_norm = 0;
+            }
         }
         // rows the full rounds do not cover (fewer than 128 * (U + 1)): they lie in ONE chunk, the last
         {
@@ -625,8 +672,8 @@ __global__ void exgemv_finish_kernel(const GemvParams prm) {
         if (prm.beta == 1.0) {
             st |= accumulate_double(acc, yv);
         } else {
-            const double p = __dmul_rn(prm.beta, yv);
-            const double e = __fma_rn(prm.beta, yv, -p);
+            double p, e;
+            scale_exact(prm.beta, yv, p, e, st);
             st |= accumulate_double(acc, p);
             if (!(e != e)) st |= accumulate_double(acc, e);
         }

@@ -24,7 +24,7 @@
 // deposits, so the result stays the exact sum whatever mix of paths was taken.
 //
 // Everything here is plain IEEE double arithmetic and integer bit casts, host + device, so the host
-// unit test (tests/test_window_host.py via oracle/window_check.cpp) exercises the very same code.
+// unit test (tests/test_window_host.py, which compiles tests/window_host_check.cpp with g++) exercises the very same code.
 #pragma once
 #include "superacc.cuh"
 

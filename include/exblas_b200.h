@@ -130,7 +130,10 @@ int exblas_b200_result_ptr(exblas_b200_handle_t handle, void** d_result);
  * pointers; with device pointers the call is asynchronous on the handle's stream (follow with
  * exblas_b200_sync to read the status flags).  fpe: 0 / 1 superaccumulators only (the reference's
  * fpe == 1 is a plain DGEMV comparator), early_exit buckets 4 / 6 / 8, else the expansion size.
- * Deviation from the reference kernels: alpha is applied (exactly); ExGEMV.FPE.cl:246 ignores it. */
+ * Deviation from the reference kernels: alpha is applied (exactly); ExGEMV.FPE.cl:246 ignores it.
+ * Domain of the exact scaling: alpha * a[i,j] and beta * y[i] are split into two doubles (TwoProductFMA), which is
+ * exact for 2^-959 <= |product| < 2^1024.  A non-zero product outside that range is dropped and reported
+ * (EXBLAS_B200_ST_TOOSMALL: the affected y[i] is not exact; EXBLAS_B200_ST_TOOLARGE), never summed inexactly. */
 int exblas_b200_exgemv(exblas_b200_handle_t handle, char trans, int64_t m, int64_t n, double alpha,
                        const double* a, int64_t lda, int64_t offseta, const double* x, int64_t incx,
                        int64_t offsetx, double beta, double* y, int64_t incy, int64_t offsety,

@@ -264,3 +264,41 @@ def test_exgemv_t_kernels(gpu, oracle):
         assert np.isinf(out[0]) and np.isnan(out[1]) and np.isfinite(out[2:]).all()
     finally:
         gpu.set_option("gemv_t_shape", 2)
+
+
+@pytest.mark.gpu
+def test_exgemv_exact_scaling_domain_is_flagged(gpu):
+    """alpha * a[i, j] / beta * y[i] that cannot be split exactly into two doubles are dropped and flagged, never summed
+    inexactly (include/exblas_b200.h: domain of the exact scaling)."""
+    import torch
+    import exblas_b200 as xb
+    m, n = 40, 64
+    a = np.full(m * n, 3.0)
+    x = np.full(n, 1.0)
+    for trans in ("N", "T"):
+        nout = m if trans == "N" else n
+        # ordinary alpha: exact, no flag
+        dy = torch.zeros(nout, dtype=torch.float64).cuda()
+        xb.exgemv(trans, m, n, 0.5, torch.from_numpy(a).cuda(), m, 0, torch.from_numpy(np.full(max(m, n), 1.0)).cuda(), 1, 0, 0.0, dy, 1, 0, 3, False, handle=gpu)
+        assert gpu.last_status() == 0 and (dy.cpu().numpy() == 1.5 * (n if trans == "N" else m)).all()
+        # alpha * a underflows: TwoProd would be inexact -> TOOSMALL
+        a2 = a.copy()
+        a2[5] = 2.0 ** -500
+        dy = torch.zeros(nout, dtype=torch.float64).cuda()
+        xb.exgemv(trans, m, n, 2.0 ** -600, torch.from_numpy(a2).cuda(), m, 0, torch.from_numpy(np.full(max(m, n), 1.0)).cuda(), 1, 0, 0.0, dy, 1, 0, 0, False, handle=gpu)
+        assert gpu.last_status() & xb.ST_TOOSMALL, trans
+        # alpha * a overflows with finite operands -> TOOLARGE, not Inf
+        a3 = a.copy()
+        a3[7] = 2.0 ** 600
+        dy = torch.zeros(nout, dtype=torch.float64).cuda()
+        xb.exgemv(trans, m, n, 2.0 ** 600, torch.from_numpy(a3).cuda(), m, 0, torch.from_numpy(np.full(max(m, n), 1.0)).cuda(), 1, 0, 0.0, dy, 1, 0, 4, False, handle=gpu)
+        st = gpu.last_status()
+        assert (st & xb.ST_TOOLARGE) and not (st & (xb.ST_POSINF | xb.ST_NAN)), (trans, st)
+    # beta * y underflow
+    dy = torch.full((m,), 2.0 ** -700, dtype=torch.float64).cuda()
+    xb.exgemv("N", m, n, 1.0, torch.from_numpy(a).cuda(), m, 0, torch.from_numpy(x).cuda(), 1, 0, 2.0 ** -400, dy, 1, 0, 0, False, handle=gpu)
+    assert gpu.last_status() & xb.ST_TOOSMALL
+    # a clean call afterwards is clean
+    dy = torch.zeros(m, dtype=torch.float64).cuda()
+    xb.exgemv("N", m, n, 1.0, torch.from_numpy(a).cuda(), m, 0, torch.from_numpy(x).cuda(), 1, 0, 0.0, dy, 1, 0, 0, False, handle=gpu)
+    assert gpu.last_status() == 0 and (dy.cpu().numpy() == 3.0 * n).all()
