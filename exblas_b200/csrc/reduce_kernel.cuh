@@ -141,7 +141,12 @@ EXB_D bool nonzero_bits(double x) {
 // a[level][m] in registers.  Two expansions per thread (F <= 4) give the FP64 pipe independent
 // TwoSum chains to overlap (elements 0,2 of a vector feed expansion 0, elements 1,3 expansion 1);
 // the exact sum does not care how summands are distributed over expansions.
-__host__ __device__ constexpr int expansions(int f) { return f <= 4 ? 2 : 1; }   // large F: registers go to the load window instead
+// (Measured, round 2: two expansions for F > 4 as well -- profiles/ab_sustained_r02.jsonl, EXB_EXP2_MAXF = 6 / 8 -- LOSE
+// 17-26 % on the large early-exit ExDOT kernels and spill in the F = 8 ones; the serial chain is not their limiter.)
+#ifndef EXB_EXP2_MAXF
+#define EXB_EXP2_MAXF 4
+#endif
+__host__ __device__ constexpr int expansions(int f) { return f <= EXB_EXP2_MAXF ? 2 : 1; }   // large F: registers go to the load window instead
 
 // Knuth TwoSum, un-contracted (ExSUM.FPE.cl:27-32): a + x = r + s exactly; a <- r, x <- s.
 EXB_D void two_sum(double& a, double& x) {
@@ -349,6 +354,55 @@ EXB_D void mul_add1(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][ex
     constexpr int first = EE ? (F > 1 ? 1 : 0) : (F > 3 ? F - 3 : 0);
     r = fpe_push1<F, EE>(a, e, first);
     if (nonzero_bits(r)) deposit(col, stride, r, status);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Touched-row tracking for the latency regime (the reference keeps imin / imax in its Superaccumulator for the same
+// reason, superaccumulator.hpp:125, superaccumulator.cpp:138-162): a launch over a few thousand elements touches 2-15 of
+// the 39 limb rows, and summing all 39 x T columns was the largest single cost of such a launch.  The kernels of
+// this regime record the exponent range of what they deposit (two integer min / max per summand, off the hot
+// streaming path) and the block merge only sums the rows that range can have touched.
+// ------------------------------------------------------------------------------------------------
+struct RowRange {
+    unsigned emin, emax;     // biased exponents of the deposited values (emin > emax: nothing deposited)
+};
+EXB_D RowRange rr_empty() { return RowRange{0x7ffu, 0u}; }
+EXB_D RowRange rr_full() { return RowRange{35u, 2010u}; }
+// a value with high / low words (hi, lo) is about to be deposited (or fed to an expansion)
+EXB_D void rr_note(RowRange& r, unsigned hi, unsigned lo) {
+    const unsigned ahi = hi & 0x7fffffffu;
+    if ((ahi | lo) == 0u) return;                              // exact zero: no deposit
+    unsigned E = ahi >> 20;
+    E = E < 35u ? 35u : (E > 2010u ? 2010u : E);               // tiny values land in limb 0; specials / too large are not deposited
+    r.emin = min(r.emin, E);
+    r.emax = max(r.emax, E);
+}
+EXB_D void rr_note(RowRange& r, double x) { rr_note(r, (unsigned)__double2hiint(x), (unsigned)__double2loint(x)); }
+// a product (its TwoProd error term reaches 105 bits below its exponent; products below 2^-935 take the integer path
+// that touches limbs 0..2)
+EXB_D void rr_note_product(RowRange& r, double x, double y) {
+    const double p = __dmul_rn(x, y);
+    const unsigned ahi = (unsigned)__double2hiint(p) & 0x7fffffffu;
+    const unsigned xz = ((unsigned)__double2hiint(x) & 0x7fffffffu) | (unsigned)__double2loint(x);
+    const unsigned yz = ((unsigned)__double2hiint(y) & 0x7fffffffu) | (unsigned)__double2loint(y);
+    if (xz == 0u || yz == 0u) return;
+    unsigned E = ahi >> 20;
+    E = E < 88u + 105u ? 35u + 105u : (E > 2010u ? 2010u : E);   // (E - 105 below is then >= 35: row 0 after the margin)
+    r.emin = min(r.emin, E - 105u);
+    r.emax = max(r.emax, E);
+}
+// limb rows [lo, hi] that deposits of values in the range can have touched; `grow` = binades by which partial sums of the
+// deposited values (expansion levels) may exceed them
+EXB_D void rr_rows(const RowRange& r, unsigned grow, unsigned& lo, unsigned& hi) {
+    if (r.emin > r.emax) {
+        lo = (unsigned)kLimbs - 1u;
+        hi = 0u;
+        return;
+    }
+    const unsigned jlo = __umulhi(r.emin + 17u, 82595525u);    // J1 of the smallest value: it touches rows J1 - 1, J1
+    const unsigned jhi = __umulhi(min(r.emax + grow, 2010u) + 17u, 82595525u);
+    lo = jlo > 2u ? jlo - 2u : 0u;                             // (one more row: residuals of an expansion reach 52 bits lower)
+    hi = jhi < (unsigned)kLimbs - 1u ? jhi : (unsigned)kLimbs - 1u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -630,15 +684,35 @@ __device__ __noinline__ bool peer_exchange(const ReduceParams& prm, WarpLimbs& x
 // Not inlined: one copy of this (cold, run-once) code serves all kernels, which keeps them small.
 __device__ __noinline__ void block_merge_and_close(const ReduceParams& prm, const unsigned stride, const unsigned smem_base,
                                                    const unsigned T, const unsigned tid, unsigned status, const bool solo,
-                                                   long long* block_lo, int* block_hi, unsigned* block_status) {
-    __syncthreads();                                       // block_status initialised; all columns final
+                                                   long long* block_lo, int* block_hi, unsigned* block_status,
+                                                   unsigned row_lo, unsigned row_hi) {
+    // block_status[0] = status flags, [1] / [2] = first / last limb row any thread of the CTA has touched
+    const unsigned warp = tid >> 5, ln = tid & 31u, nwarps = T >> 5;
+    if (tid == 0) {
+        block_status[0] = 0u;
+        block_status[1] = (unsigned)kLimbs - 1u;
+        block_status[2] = 0u;
+    }
+    __syncthreads();
+    row_lo = __reduce_min_sync(kFullWarp, row_lo);
+    row_hi = __reduce_max_sync(kFullWarp, row_hi);
+    if (ln == 0) {
+        atomicMin(&block_status[1], row_lo);
+        atomicMax(&block_status[2], row_hi);
+    }
+    if (tid < (unsigned)kLimbs) {
+        block_lo[tid] = 0;
+        block_hi[tid] = 0;
+    }
+    __syncthreads();                                       // row range and block sums initialised; all columns final
     if (status) {
         if (solo) atomicOr(block_status, status);
         else atomicOr(&prm.ws->status, status);
     }
-    const unsigned warp = tid >> 5, ln = tid & 31u, nwarps = T >> 5;
+    row_lo = block_status[1];
+    row_hi = block_status[2];
 #pragma unroll 1
-    for (unsigned j = warp; j < (unsigned)kLimbs; j += nwarps) {      // (rolled on purpose: this code runs once, from a cold instruction cache)
+    for (unsigned j = row_lo + warp; j <= row_hi; j += nwarps) {      // (rolled on purpose: this code runs once, from a cold instruction cache)
         long long lo;
         int hi;
         row_sum_split(smem_base + j * stride, T, ln, lo, hi);
@@ -737,11 +811,15 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
     constexpr int kSlack = 2 * kM * (F + 2) + 16;          // room for the flush of the expansions
     __shared__ long long block_lo[kLimbs];
     __shared__ int block_hi[kLimbs];
-    __shared__ unsigned block_status;
+    __shared__ unsigned block_status[3];
     // Latency regime: a single CTA reducing into an empty workspace publishes straight from shared
     // memory -- no global atomics, fence or ticket.
     const bool solo = (gridDim.x == 1) && prm.fresh && prm.finalize;
-    if (tid == 0) block_status = 0;
+    // Without an unrolled body (vectors below ~2^20 elements) everything this CTA deposits passes through the loops
+    // below, which then record its exponent range: the merge only sums the limb rows that range can have touched.
+    // (ExSUM only: in the ExDOT instantiations the extra live state spilled registers of the streaming loops, -8 %.)
+    const bool track = !DOT && prm.iters == 0;
+    RowRange rr = track ? rr_empty() : rr_full();
     EXB_PHASE(2);
 
     // ---------------- 1. remainder of the vector region ----------------
@@ -771,6 +849,10 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
                 for (int u = 0; u < UR; ++u) {
                     if (r + u * gthreads < nrem) {
                         double x4[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                        if (!DOT && track) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) rr_note(rr, x4[q]);
+                        }
                         if (DOT) {
                             const double y4[4] = {vb[DOT ? u : 0].x, vb[DOT ? u : 0].y, vb[DOT ? u : 0].z, vb[DOT ? u : 0].w};
                             if (F == 0 || direct) {
@@ -824,6 +906,10 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
                 xa[j] = ldg64(prm.a + idx * prm.inca);
                 if (DOT) xb[DOT ? j : 0] = ldg64(prm.b + idx * prm.incb);
             }
+            if (!DOT && track) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rr_note(rr, xa[j]);
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 double x4[4] = {xa[4 * h], xa[4 * h + 1], xa[4 * h + 2], xa[4 * h + 3]};
@@ -844,6 +930,7 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
         }
         for (; k < nscalar; k += gthreads) {
             const long long idx = k < prm.head ? k : k + body;
+            if (!DOT && track) rr_note(rr, prm.a[idx * prm.inca]);
             if (DOT) mul_add1<F, EE>(col, stride, a, status, prm.a[idx * prm.inca], prm.b[idx * prm.incb]);
             else add1<F, EE>(col, stride, a, status, prm.a[idx * prm.inca]);
             since_norm += kDepPerElem;
@@ -861,7 +948,9 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
             for (int m = 0; m < kM; ++m) deposit_sum(col, stride, a[i][m], status);
     }
     EXB_PHASE(4);
-    block_merge_and_close(prm, stride, smem_base, T, tid, status, solo, block_lo, block_hi, &block_status);
+    unsigned row_lo, row_hi;
+    rr_rows(rr, F > 0 ? 64u : 0u, row_lo, row_hi);        // partial sums in the expansions may grow beyond the largest summand
+    block_merge_and_close(prm, stride, smem_base, T, tid, status, solo, block_lo, block_hi, block_status, row_lo, row_hi);
 }
 
 // (Measured and rejected, round 1: moving the thrash bypass or the expansion walk of THIS kernel into out-of-line
@@ -1502,13 +1591,14 @@ __global__ void __launch_bounds__(512, 1) exblas_small_kernel(const __grid_const
     extern __shared__ long long smem[];
     __shared__ long long block_lo[kLimbs];
     __shared__ int block_hi[kLimbs];
-    __shared__ unsigned block_status;
+    __shared__ unsigned block_status[3];
     const unsigned T = blockDim.x;
     const unsigned tid = threadIdx.x;
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned stride = 8u * T;
     const unsigned col = smem_base + 8u * tid;
     EXB_PHASE(0);
+    RowRange rr = rr_empty();
     Vec4 va[4];
     Vec4 vb[DOT ? 4 : 1];
     const long long nvec = prm.nvec;
@@ -1520,7 +1610,6 @@ __global__ void __launch_bounds__(512, 1) exblas_small_kernel(const __grid_const
             if (DOT) vb[DOT ? u : 0] = ldg256(prm.b + prm.head + 4 * r);
         }
     }
-    if (tid == 0) block_status = 0;
 #pragma unroll 13
     for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
     unsigned status = 0;
@@ -1533,8 +1622,10 @@ __global__ void __launch_bounds__(512, 1) exblas_small_kernel(const __grid_const
             for (int k = 0; k < 4; ++k) {
                 if (DOT) {
                     const double y4[4] = {vb[DOT ? u : 0].x, vb[DOT ? u : 0].y, vb[DOT ? u : 0].z, vb[DOT ? u : 0].w};
+                    rr_note_product(rr, x4[k], y4[k]);
                     mul_add1<0, false>(col, stride, none, status, x4[k], y4[k]);
                 } else {
+                    rr_note(rr, x4[k]);
                     deposit(col, stride, x4[k], status);
                 }
             }
@@ -1542,9 +1633,14 @@ __global__ void __launch_bounds__(512, 1) exblas_small_kernel(const __grid_const
     }
     EXB_PHASE(1);
     // scalar part: alignment head, tail, or the whole strided / misaligned vector (out of line: usually absent)
-    if (prm.n != 4 * nvec) status |= small_scalar_part<DOT>(prm, col, stride, tid, T);
+    if (prm.n != 4 * nvec) {
+        status |= small_scalar_part<DOT>(prm, col, stride, tid, T);
+        rr = rr_full();                                    // (rare path: not tracked)
+    }
     EXB_PHASE(4);
-    block_merge_and_close(prm, stride, smem_base, T, tid, status, true, block_lo, block_hi, &block_status);
+    unsigned row_lo, row_hi;
+    rr_rows(rr, 0u, row_lo, row_hi);
+    block_merge_and_close(prm, stride, smem_base, T, tid, status, true, block_lo, block_hi, block_status, row_lo, row_hi);
 }
 
 // Multi-GPU epilogue: the result slot's limbs and flag counters have been summed over ranks by an

@@ -1,6 +1,8 @@
-"""Turn the scratch ncu captures under gpurun_out/ into the committed summaries under profiles/.
+"""Turn ncu captures (.ncu-rep, tens of MB each) into the small text summaries that are committed under profiles/.
 
-    python scripts/make_profiles.py r01
+    python scripts/make_profiles.py r02 [dir with the .ncu-rep files = gpurun_out] [output dir = profiles]
+
+(scripts/ncu_round.sh runs it ON the GPU box, so that only the summaries travel back.)
 
 For each gpurun_out/prof_<round>_*.ncu-rep: profiles/<name>.metrics.txt (key raw metrics) and
 profiles/<name>.hot_sass.txt (the 40 instructions with the most stall samples).  Also copies the
@@ -10,7 +12,8 @@ import csv, glob, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
-out_dir = os.path.join(ROOT, "profiles")
+in_dir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out")
+out_dir = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
@@ -25,7 +28,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__pcsamp_sample_count"]
 
 traffic = {}
-for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{rnd}_*.ncu-rep"))):
+for rep in sorted(glob.glob(os.path.join(in_dir, f"prof_{rnd}_*.ncu-rep"))):
     name = os.path.basename(rep)[:-len(".ncu-rep")]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -74,31 +77,33 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{rnd}_*.ncu-
     open(os.path.join(out_dir, name + ".hot_sass.txt"), "w").write("\n".join(hl) + "\n")
     print("wrote", name)
 
-# bench.py looks the dominant kernel's traffic up by "<op>_2p30"
+# bench.py looks the traffic of a variant up by "op|dist|fpe|ee|log2n" (roofline.traffic); the capture names are
+# <op>_fpe<F>[ee]_<dist>_2p<log2n>
+import re
 old_tj = {}
-tpath = os.path.join(out_dir, "traffic.json")
+tpath = os.path.join(ROOT, "profiles", "traffic.json")
 if os.path.exists(tpath):          # captures of earlier sessions whose .ncu-rep files are gone: keep their entries
     try:
         old_tj = json.load(open(tpath))
     except Exception:
         old_tj = {}
-traffic = {**old_tj.get("all", {}), **traffic}
-tj = {}
+tj = {k: v for k, v in old_tj.items() if "|" in k}
+allc = {**old_tj.get("all", {}), **traffic}
 for k, v in traffic.items():
-    if k.startswith("exsum") and "logu" in k:
-        tj["exsum_2p30"] = v
-    if k.startswith("exdot"):
-        tj["exdot_2p30"] = v
-tj["all"] = traffic
+    m = re.match(r"(exsum|exdot)_fpe(\d+)(ee)?_(.+)_2p(\d+)$", k)
+    if m:
+        dist = {"cancel": "illcond"}.get(m.group(4), m.group(4))
+        tj[f"{m.group(1)}|{dist}|{m.group(2)}|{1 if m.group(3) else 0}|{m.group(5)}"] = v
+tj["all"] = allc
 json.dump(tj, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
 
-lc = os.path.join(ROOT, "gpurun_out", f"launches_{rnd}.csv")
+lc = os.path.join(in_dir, f"launches_{rnd}.csv")
 if os.path.exists(lc):
     rows = [r for r in csv.reader(open(lc)) if len(r) > 5]
     hdr = rows[0]
     i_name, i_val, i_unit, i_id = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("ID")
-    sel = [r for r in rows[1:] if "exblas" in r[i_name]]
-    other = [r for r in rows[1:] if "exblas" not in r[i_name]]
+    sel = [r for r in rows[1:] if "exblas" in r[i_name] or "exb::" in r[i_name]]
+    other = [r for r in rows[1:] if r not in sel]
     def us(r):
         v = float(r[i_val].replace(",", ""))
         return v * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(r[i_unit], 1)
@@ -106,7 +111,7 @@ if os.path.exists(lc):
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline\n")
         f.write("# exblas kernels only (the other launches are torch kernels generating the synthetic input, outside the timed region)\n")
         f.write(f"# exblas launches: {len(sel)}, total {sum(map(us, sel)):.1f} us; torch set-up launches: {len(other)}, total {sum(map(us, other)):.1f} us\n")
-        f.write("# timed region = the last 6 launches: 100 % exblas_reduce_kernel\n")
+        f.write("# timed region = the last 6 exblas_reduce_kernel launches (2 steps x FPE 3, 4, 8); before them: warm-up steps, the per-FPE burst timing and the two microbenchmarks\n")
         f.write("id,kernel,duration_us\n")
         for r in sel:
             f.write(f"{r[i_id]},\"{r[i_name]}\",{us(r):.2f}\n")
