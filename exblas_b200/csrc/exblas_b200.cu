@@ -225,6 +225,8 @@ struct exblas_b200_handle_s {
     Result* h_res = nullptr;                // pinned
     double* d_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][a|b]
     int64_t stage_elems = 0;
+    void* d_seg_scratch = nullptr;          // batched reductions: one SegScratch per warp range (self-cleaning)
+    size_t seg_scratch_bytes = 0;
     long long* d_gemv_scratch = nullptr;    // [parts][39][m] limbs + [parts][m] status words
     size_t gemv_scratch_bytes = 0;
     int64_t opt_block_threads = kMaxT;
@@ -774,7 +776,31 @@ typedef void (*seg_fn)(const SegParams);
 constexpr int kSegT = 256;
 
 int segments_device(exblas_b200_handle_t h, const double* a, const double* b, const int* gather, const int64_t* seg,
-                    int64_t nseg, int round_mode, double* results, uint32_t* statuses) {
+                    int64_t nseg, int64_t total_hint, int round_mode, double* results, uint32_t* statuses) {
+    const int nwarps = kSegT / 32;
+    // every warp of the grid streams an equal share of the ELEMENTS; enough CTAs for two per SM unless the input is small
+    // (total_hint = number of elements when the caller knows it, else -1)
+    int64_t grid = 2 * (int64_t)h->num_sms;
+    // A segment longer than a range is reduced piecewise, one piece per warp; every piece adds limbs of magnitude
+    // below 2^52 + 2^11 to one of two 64-bit scratch accumulators (even / odd warps), so at most 2 x 2047 warps may run.
+    if (grid * nwarps > 4080) grid = 4080 / nwarps;
+    if (total_hint >= 0) {
+        int64_t want = (total_hint + nwarps * 2048 - 1) / (nwarps * 2048);      // ~2048 elements per warp at least
+        const int64_t by_seg = (nseg + nwarps * 256 - 1) / (nwarps * 256);       // (many empty segments still need writers)
+        if (want < by_seg) want = by_seg;
+        if (want < 1) want = 1;
+        if (grid > want) grid = want;
+    }
+    const size_t need = (size_t)grid * nwarps * sizeof(SegScratch);
+    if (need > h->seg_scratch_bytes) {
+        if (h->d_seg_scratch) cudaFree(h->d_seg_scratch);
+        h->d_seg_scratch = nullptr;
+        h->seg_scratch_bytes = 0;
+        const size_t cap = (size_t)2 * h->num_sms * nwarps * sizeof(SegScratch);
+        CK(cudaMalloc(&h->d_seg_scratch, cap));
+        CK(cudaMemsetAsync(h->d_seg_scratch, 0, cap, h->stream));       // self-cleaning afterwards (the last piece of a segment clears its slot)
+        h->seg_scratch_bytes = cap;
+    }
     SegParams p;
     memset(&p, 0, sizeof(p));
     p.a = a;
@@ -785,13 +811,11 @@ int segments_device(exblas_b200_handle_t h, const double* a, const double* b, co
     p.results = results;
     p.statuses = statuses;
     p.ws = h->d_ws;
+    p.scratch = (SegScratch*)h->d_seg_scratch;
     p.round_mode = round_mode;
     seg_fn fn = b ? (gather ? exblas_segments_kernel<true, true, kSegT> : exblas_segments_kernel<true, false, kSegT>)
                   : exblas_segments_kernel<false, false, kSegT>;
-    const int nwarps = kSegT / 32;
-    const size_t smem = ((size_t)kSegT * kLimbs + 40 * (size_t)nwarps) * sizeof(long long);
-    int64_t grid = (nseg + nwarps - 1) / nwarps;
-    if (grid > 2 * (int64_t)h->num_sms) grid = 2 * (int64_t)h->num_sms;
+    const size_t smem = (size_t)kSegT * kLimbs * sizeof(long long);
     CK(allow_big_smem((const void*)fn, h->device));
     void* args[] = {(void*)&p};
     CK(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3((unsigned)kSegT), args, smem, h->stream));
@@ -810,7 +834,7 @@ int segments_any(exblas_b200_handle_t h, const double* a, const double* b, const
     CK(cudaSetDevice(h->device));
     const bool dev = is_device_pointer(results);
     if (dev) {
-        int rc = segments_device(h, a, b, (const int*)gather, seg, nseg, round_mode, results, statuses);
+        int rc = segments_device(h, a, b, (const int*)gather, seg, nseg, -1, round_mode, results, statuses);
         if (rc) return rc;
     } else {
         // host operands (what the reference's callers hold): validate the offsets, stage everything once
@@ -850,7 +874,7 @@ int segments_any(exblas_b200_handle_t h, const double* a, const double* b, const
             if (nbv) CK(cudaMemcpyAsync(db, b, nbv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             if (dg) CK(cudaMemcpyAsync(dg, gather, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(ds, seg, (size_t)(nseg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-            int r2 = segments_device(h, da, b ? db : nullptr, dg, ds, nseg, round_mode, dr, dst);
+            int r2 = segments_device(h, da, b ? db : nullptr, dg, ds, nseg, total - seg[0], round_mode, dr, dst);
             if (r2) return r2;
             CK(cudaMemcpyAsync(results, dr, (size_t)nseg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             if (statuses) CK(cudaMemcpyAsync(statuses, dst, (size_t)nseg * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -958,6 +982,7 @@ int exblas_b200_destroy(exblas_b200_handle_t h) {
     }
     if (h->d_mailbox) cudaFree(h->d_mailbox);
     if (h->d_gemv_scratch) cudaFree(h->d_gemv_scratch);
+    if (h->d_seg_scratch) cudaFree(h->d_seg_scratch);
     if (h->d_phase) cudaFree(h->d_phase);
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_res) cudaFree(h->d_res);
@@ -984,7 +1009,7 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
         h->opt_block_threads = value;
         h->opt_shape_fixed = true;
     } else if (!strcmp(name, "blocks")) {
-        if (value < 0 || value > 2048) return EXBLAS_B200_EINVAL;    // 2048 partials of < 2^52 + 2^10 fit a limb
+        if (value < 0 || value > 2040) return EXBLAS_B200_EINVAL;    // 2040 partials of magnitude < 2^52 + 2^10 (+ a pending normalised sum) fit a 64-bit limb
         h->opt_blocks = value;
         h->opt_shape_fixed = true;
     } else if (!strcmp(name, "auto_shape")) {                        // back to the size-dependent launch shape

@@ -116,3 +116,51 @@ def test_segments_status_per_segment(gpu):
     assert np.isposinf(got[0]) and np.isnan(got[1]) and got[2] == 80.0
     assert st[0] == xb.ST_POSINF and st[1] == xb.ST_NAN and st[2] == 0 and st[3] == xb.ST_TOOLARGE
     assert gpu.last_status() == (xb.ST_POSINF | xb.ST_NAN | xb.ST_TOOLARGE)
+
+
+@pytest.mark.gpu
+def test_segments_any_decomposition(gpu, oracle):
+    """The element range is cut into one piece per warp of the grid: segments far longer than a piece are reduced piecewise
+    (scratch accumulators + last-arriver finish), runs of short segments take the lane-per-segment path, and everything in
+    between is mixed.  Every result must still be the oracle's bits; leading / trailing / interior empty segments included."""
+    import torch
+    rng = np.random.default_rng(11)
+    layouts = {
+        "two_huge": [1_500_000, 0, 2_000_003],
+        "huge_then_short": [3_000_000] + [7] * 500 + [0] * 40,
+        "short_runs_and_long": [0, 0] + list(rng.integers(1, 65, size=3000)) + [100_000] + list(rng.integers(60, 70, size=400))
+                               + [65, 64, 63, 1, 0, 0, 0],
+        "all_16": [16] * 50_000,
+        "thresholds": [63, 64, 65, 127, 128, 129, 3, 3, 3, 3, 64, 64, 64, 64, 65, 2047, 2048, 2049, 1, 1, 1],
+        "few_elements": [1, 0, 2, 0, 0, 3],
+    }
+    for name, lengths in layouts.items():
+        seg = offsets(np.array(lengths, dtype=np.int64))
+        total = int(seg[-1])
+        for kind in ("wide", "narrow"):
+            a = make_data(max(total, 1), kind, 21)
+            b = make_data(max(total, 1), "illcond", 22)
+            da, db, ds = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(seg).cuda()
+            gs, st = gpu.exsum_segments(da, ds, want_status=True)
+            gd = gpu.exdot_segments(da, db, ds, round_mode=1)
+            gs, gd = gs.cpu().numpy(), gd.cpu().numpy()
+            assert int(st.abs().sum()) == 0
+            check = range(len(lengths)) if len(lengths) <= 600 else list(rng.choice(len(lengths), size=300, replace=False)) + [0, len(lengths) - 1]
+            for i in check:
+                lo, hi = int(seg[i]), int(seg[i + 1])
+                ws = oracle.exsum(a[lo:hi], fpe=0)[0] if hi > lo else 0.0
+                wd = oracle.exdot(a[lo:hi], b[lo:hi], fpe=0, round_mode=1)[0] if hi > lo else 0.0
+                assert np.float64(gs[i]).view(np.uint64) == np.float64(ws).view(np.uint64), (name, kind, i, lengths[i], "sum")
+                assert np.float64(gd[i]).view(np.uint64) == np.float64(wd).view(np.uint64), (name, kind, i, lengths[i], "dot")
+    # a run of launches leaves the scratch accumulators clean: same answer every time
+    seg = offsets(np.array(layouts["two_huge"], dtype=np.int64))
+    a = make_data(int(seg[-1]), "wide", 23)
+    da, ds = torch.from_numpy(a).cuda(), torch.from_numpy(seg).cuda()
+    first = gpu.exsum_segments(da, ds).cpu().numpy()
+    for _ in range(5):
+        assert (gpu.exsum_segments(da, ds).cpu().numpy().view(np.uint64) == first.view(np.uint64)).all()
+    # offsets that do not start at zero
+    seg2 = seg + 0
+    seg2[0] = 12345
+    got = gpu.exsum_segments(da, torch.from_numpy(seg2).cuda()).cpu().numpy()
+    assert got[0] == oracle.exsum(a[12345:int(seg2[1])], fpe=0)[0] and got[2] == first[2]
