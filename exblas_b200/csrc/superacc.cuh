@@ -482,6 +482,60 @@ EXB_D void deposit4(unsigned col, unsigned stride, double x0, double x1, double 
     }
 }
 
+// A product with its TwoProd error term, p + e = a * b exactly, into THREE adjacent limbs instead of two deposits of two
+// limbs each (round 2): e is at most half an ulp of p, so its digits fall on the two limbs below p's top limb and the
+// middle limb is shared -- 3 instead of 4 read-modify-writes per product (12 instead of 16 shared-memory wavefronts per
+// warp-product), which is what wide-range ExDOT / ExGEMV data are bound by.
+// Grid: J = floor((E + 16) / 52), so that xs = |p| / 2^(52 J - 1040) lies in [2^s, 2^(s+1)) with s in [1, 52]
+// (deposit_fast uses s in [0, 51]; s >= 1 is what makes the last digit of e an integer, see below).
+//   p:  D1 = rint(xs) via the 2^52 magic add for s <= 51; for s = 52 xs IS a 53-bit integer: D1 = its mantissa, no
+//       remainder (selected without a branch);  D0 = (xs - D1) 2^52
+//   e:  es = e / 2^(52 J - 1040), |es| <= 2^(s-53) <= 1/2:   E1 = rint(es 2^52) = bits(es + 1.5) - bits(1.5),
+//       r3 = es - E1 2^-52 (exact, |r3| <= 2^-53),           E0 = r3 2^104 = bits(r3 + 1.5 2^-52) - bits(1.5 2^-52)
+//   limbs:  J += +-D1 (< 2^53: two digits' worth, which is what the ExDOT deposit budget counts per product),
+//           J - 1 += +-D0 + E1,   J - 2 += E0
+// E0 is an integer because e is a multiple of 2^(exp(p) - 105), i.e. of 2^(s - 105) on this grid, and s >= 1.
+// p must be large enough for e to be a normal number: product3_ok().  Checked against exact rational arithmetic on
+// 2 x 10^5 random products (all exponents, exact products, short mantissas) before it went to the GPU.
+EXB_D bool product3_ok(unsigned phi) {
+    return ((phi & 0x7fffffffu) >> 20) - 200u < kELim - 200u;             // 2^-823 <= |p| < 2^988
+}
+EXB_D void deposit_product3(unsigned col, unsigned stride, double p, double e) {
+    const unsigned hi = (unsigned)__double2hiint(p), lo = (unsigned)__double2loint(p);
+    const unsigned ahi = hi & 0x7fffffffu;
+    const unsigned E = ahi >> 20;
+    const unsigned J = __umulhi(E + 16u, 82595525u);                      // >= 4 here
+    const unsigned shift = J * (52u << 20) - (1040u << 20);               // exponent-field distance to the limb-J grid
+    const unsigned xhi = ahi - shift;                                     // exponent field s + 1023, s in [1, 52]
+    const double xs = __hiloint2double((int)xhi, (int)lo);
+    const bool wide = xhi >= ((52u + 1023u) << 20);                       // s == 52: xs is an integer of 53 bits
+    const double t = __dadd_rn(xs, 4503599627370496.0);                   // 2^52 + D1 (s <= 51)
+    const double xr = __dsub_rn(t, 4503599627370496.0);
+    double rem = wide ? 0.0 : __dsub_rn(xs, xr);                          // exact, in [-0.5, 0.5]
+    rem = __hiloint2double(__double2hiint(rem) ^ (int)(hi & 0x80000000u), __double2loint(rem));
+    const double t2 = __dadd_rn(rem, 1.5);
+    // D1 as an unsigned integer: bits(t) - bits(2^52), or the 53-bit mantissa itself
+    const unsigned long long mant = ((unsigned long long)((ahi & 0xfffffu) | 0x100000u) << 32) | lo;
+    const unsigned long long d1 = wide ? mant : (unsigned long long)__double_as_longlong(t) - 0x4330000000000000ull;
+    // e on the same grid (its own sign stays in place; a zero stays a zero)
+    const unsigned ehi = (unsigned)__double2hiint(e), elo = (unsigned)__double2loint(e);
+    const bool ez = ((ehi & 0x7fffffffu) | elo) == 0u;
+    const double es = ez ? 0.0 : __hiloint2double((int)(ehi - shift), (int)elo);
+    const double t3 = __dadd_rn(es, 1.5);
+    const double r3 = __dsub_rn(es, __dsub_rn(t3, 1.5));
+    const double t4 = __dadd_rn(r3, 3.3306690738754696e-16);              // 1.5 * 2^-52
+    const unsigned long long dmid = (unsigned long long)__double_as_longlong(t2) + (unsigned long long)__double_as_longlong(t3) -
+                                    2ull * 0x3FF8000000000000ull;
+    const unsigned long long dlow = (unsigned long long)__double_as_longlong(t4) - 0x3CB8000000000000ull;
+    const unsigned long long sm = (unsigned long long)((long long)(int)hi >> 31);     // all ones when p < 0
+    const unsigned a2 = col + J * stride;
+    const unsigned a1 = a2 - stride, a0 = a1 - stride;
+    const unsigned long long v0 = lds64(a0), v1 = lds64(a1), v2 = lds64(a2);
+    sts64(a0, v0 + dlow);
+    sts64(a1, v1 + dmid);
+    sts64(a2, v2 + (d1 ^ sm) - sm);
+}
+
 // Bound a thread-private column in place WITHOUT a carry chain: every limb keeps its low 52 bits
 // and receives the carry-save bits of the limb below (one step, no propagation).  The value is
 // unchanged and afterwards |limb| < 2^52 + 2^11, which is all the deposit budget (2046 more
