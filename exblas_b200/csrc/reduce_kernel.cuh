@@ -276,22 +276,6 @@ __device__ __noinline__ unsigned product_slow(unsigned col, unsigned stride, dou
     return st;
 }
 
-// four products whose p is outside the three-limb fast range (below 2^-823, zero, or already diverted): the ordinary
-// checked deposits of both parts, out of line
-__device__ __noinline__ unsigned deposit_products_slow(unsigned col, unsigned stride, double p0, double p1, double p2, double p3,
-                                                       double e0, double e1, double e2, double e3) {
-    unsigned status = 0;
-    deposit(col, stride, p0, status);
-    deposit(col, stride, e0, status);
-    deposit(col, stride, p1, status);
-    deposit(col, stride, e1, status);
-    deposit(col, stride, p2, status);
-    deposit(col, stride, e2, status);
-    deposit(col, stride, p3, status);
-    deposit(col, stride, e3, status);
-    return status;
-}
-
 // Four products: TwoProductFMA (ExDOT.FPE.cl:25-29), then p through all levels and the error terms
 // through the lower levels (ExDOT.FPE.cl:254-258: level F-3; ExDOT.FPE.EX.4.cl: level 1 with early
 // exit).  F == 0: both parts are deposited directly (ExDOT.Superacc.cl:244-253).
@@ -319,18 +303,20 @@ EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][exp
     }
     if (F == 0) {
 #ifndef EXB_NO_PRODUCT3
-        // p and its error term share their middle limb: three read-modify-writes per product instead of four
-        if (product3_ok((unsigned)__double2hiint(p[0])) & product3_ok((unsigned)__double2hiint(p[1])) &
-            product3_ok((unsigned)__double2hiint(p[2])) & product3_ok((unsigned)__double2hiint(p[3]))) {
+        // p and its error term share their middle limb: three read-modify-writes per product instead of four.  (In the
+        // streaming loops only -- UNIFORM: in the out-of-line miss paths of the window kernels the extra code cost the
+        // surrounding loops registers, -6 % on ill-conditioned ExDOT.)
+        // (Exact zero products -- zeros in the data, products diverted above -- pass the test: they add zeros.)
+        if (UNIFORM)
+        if (product3_ok((unsigned)__double2hiint(p[0]), (unsigned)__double2loint(p[0])) & product3_ok((unsigned)__double2hiint(p[1]), (unsigned)__double2loint(p[1])) &
+            product3_ok((unsigned)__double2hiint(p[2]), (unsigned)__double2loint(p[2])) & product3_ok((unsigned)__double2hiint(p[3]), (unsigned)__double2loint(p[3]))) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) deposit_product3(col, stride, p[k], e[k]);
             return 0;
         }
-        status |= deposit_products_slow(col, stride, p[0], p[1], p[2], p[3], e[0], e[1], e[2], e[3]);   // rare: tiny / zero / dropped products
-#else
+#endif
         deposit4<false>(col, stride, p[0], p[1], p[2], p[3], status);
         deposit4<false>(col, stride, e[0], e[1], e[2], e[3], status);     // zeros take the (cheap) slow path
-#endif
         return 0;
     }
     int cnt = 0;

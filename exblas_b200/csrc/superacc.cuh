@@ -497,16 +497,18 @@ EXB_D void deposit4(unsigned col, unsigned stride, double x0, double x1, double 
 // E0 is an integer because e is a multiple of 2^(exp(p) - 105), i.e. of 2^(s - 105) on this grid, and s >= 1.
 // p must be large enough for e to be a normal number: product3_ok().  Checked against exact rational arithmetic on
 // 2 x 10^5 random products (all exponents, exact products, short mantissas) before it went to the GPU.
-EXB_D bool product3_ok(unsigned phi) {
-    return ((phi & 0x7fffffffu) >> 20) - 200u < kELim - 200u;             // 2^-823 <= |p| < 2^988
+EXB_D bool product3_ok(unsigned phi, unsigned plo) {
+    const unsigned ahi = phi & 0x7fffffffu;
+    return ((ahi >> 20) - 200u < kELim - 200u) | ((ahi | plo) == 0u);     // 2^-823 <= |p| < 2^988, or an exact zero (adds zeros)
 }
 EXB_D void deposit_product3(unsigned col, unsigned stride, double p, double e) {
     const unsigned hi = (unsigned)__double2hiint(p), lo = (unsigned)__double2loint(p);
     const unsigned ahi = hi & 0x7fffffffu;
     const unsigned E = ahi >> 20;
-    const unsigned J = __umulhi(E + 16u, 82595525u);                      // >= 4 here
+    const bool pz = ahi == 0u;                                            // an exact zero (its error term is zero too): digits 0, 0, 0 into limbs 0..2
+    const unsigned J = pz ? 2u : __umulhi(E + 16u, 82595525u);            // >= 4 otherwise
     const unsigned shift = J * (52u << 20) - (1040u << 20);               // exponent-field distance to the limb-J grid
-    const unsigned xhi = ahi - shift;                                     // exponent field s + 1023, s in [1, 52]
+    const unsigned xhi = pz ? 0u : ahi - shift;                           // exponent field s + 1023, s in [1, 52]
     const double xs = __hiloint2double((int)xhi, (int)lo);
     const bool wide = xhi >= ((52u + 1023u) << 20);                       // s == 52: xs is an integer of 53 bits
     const double t = __dadd_rn(xs, 4503599627370496.0);                   // 2^52 + D1 (s <= 51)
