@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
         if constexpr (unit_alpha) {
             if (direct) {
                 double none[1][expansions(0)];
-                mul_add4<0, false, true>(col, stride, none, status, xa, xb);
+                mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
             } else {
                 deposits += mul_add4<F, EE, true>(col, stride, a, status, xa, xb);
             }
@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
             for (int k = 0; k < 4; ++k) scale_exact(prm.alpha, xa[k], p1[k], e1[k], status);
             if (direct) {
                 double none[1][expansions(0)];
-                mul_add4<0, false, true>(col, stride, none, status, p1, xb);
-                mul_add4<0, false, true>(col, stride, none, status, e1, xb);
+                mul_add4<0, false, true, false>(col, stride, none, status, p1, xb);
+                mul_add4<0, false, true, false>(col, stride, none, status, e1, xb);
             } else {
                 deposits += mul_add4<F, EE, true>(col, stride, a, status, p1, xb);
                 deposits += mul_add4<F, EE, true>(col, stride, a, status, e1, xb);
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
                 lds128(xaddr + 16u, xb[2], xb[3]);
                 xaddr += 32u;
                 double none[1][expansions(0)];
-                mul_add4<0, false, true>(col, stride, none, status, xa, xb);
+                mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
             }
             since_norm += 8 * U;
             if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
                     load_x(xaddr, xb[0], xb[1], xb[2], xb[3]);
                     xaddr += 1024u;
                     double none[1][expansions(0)];
-                    mul_add4<0, false, true>(col, stride, none, status, xa, xb);
+                    mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
                 }
                 w.st = status;
                 since_norm += 8 * U;

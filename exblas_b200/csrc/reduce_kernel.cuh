@@ -279,7 +279,7 @@ __device__ __noinline__ unsigned product_slow(unsigned col, unsigned stride, dou
 // Four products: TwoProductFMA (ExDOT.FPE.cl:25-29), then p through all levels and the error terms
 // through the lower levels (ExDOT.FPE.cl:254-258: level F-3; ExDOT.FPE.EX.4.cl: level 1 with early
 // exit).  F == 0: both parts are deposited directly (ExDOT.Superacc.cl:244-253).
-template <int F, bool EE, bool UNIFORM>
+template <int F, bool EE, bool UNIFORM, bool P3 = UNIFORM>
 EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][expansions(F)], unsigned& status,
                    const double (&x)[4], const double (&y)[4]) {
     double p[4], e[4];
@@ -304,10 +304,11 @@ EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][exp
     if (F == 0) {
 #ifndef EXB_NO_PRODUCT3
         // p and its error term share their middle limb: three read-modify-writes per product instead of four.  (In the
-        // streaming loops only -- UNIFORM: in the out-of-line miss paths of the window kernels the extra code cost the
-        // surrounding loops registers, -6 % on ill-conditioned ExDOT.)
+        // streaming loops of the ExSUM / ExDOT / batched kernels only -- P3: in the out-of-line miss paths of the window
+        // kernels and in the ExGEMV window kernels' fallback bodies the extra code cost the surrounding window loops
+        // registers: -6 % on ill-conditioned ExDOT, -15 % on ExGEMV 'T'.)
         // (Exact zero products -- zeros in the data, products diverted above -- pass the test: they add zeros.)
-        if (UNIFORM)
+        if (P3)
         if (product3_ok((unsigned)__double2hiint(p[0]), (unsigned)__double2loint(p[0])) & product3_ok((unsigned)__double2hiint(p[1]), (unsigned)__double2loint(p[1])) &
             product3_ok((unsigned)__double2hiint(p[2]), (unsigned)__double2loint(p[2])) & product3_ok((unsigned)__double2hiint(p[3]), (unsigned)__double2loint(p[3]))) {
 #pragma unroll
