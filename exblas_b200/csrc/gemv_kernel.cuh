@@ -429,6 +429,8 @@ EXB_D void cp_async8(unsigned dst, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 EXB_D void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// CTA-wide barrier 1 with an explicit arrival count: may be reached from different program points by different warps
+EXB_D void bar_sync_named(unsigned nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 EXB_D double lds_f64(unsigned addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -541,60 +543,67 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
             const int chunk = (int)(r / RPC);
             if (r % RPC == 0) {
                 cp_async_wait_all();
-                __syncthreads();                                                     // chunk resident; buffer (chunk + 1) & 1 is free
+                bar_sync_named(T);                                                   // chunk resident; buffer (chunk + 1) & 1 is free
                 if (chunk + 1 < nchunks) stage(chunk + 1);
             }
             return xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u) + (unsigned)(r % RPC) * (128u * U * 8u) + (VEC ? 32u : 8u) * lane;
         };
-        // ONE loop over the rounds with ONE call site of chunk_gate (its __syncthreads must be reached by every warp from
-        // the same program point, whatever mode the warp is in).  Per warp: register-window mode until two rounds in a
-        // row mostly miss (then ordinary deposits for the rest of this column and the next 7 columns).
-        bool windowed = skip_window == 0;
-        if (!windowed) --skip_window;
-        int bad = 0;
-        for (long long r = 0; r < rounds; ++r) {
+        // Two loops (window mode, then -- for a warp whose column turns out wide -- plain deposits); each calls chunk_gate
+        // once per round.  Which loop a warp is in depends on its own data, so the CTA-wide hand-over of the x chunks is a
+        // NAMED barrier with an explicit thread count (bar.sync 1, T): PTX pairs arrivals by barrier id whatever code path
+        // they come from, which __syncthreads() in warp-divergent control flow does not promise.  (One merged loop with a
+        // single call site was measured 6 % slower: both bodies in one loop cost the window path registers.)
+        long long r = 0;
+        // ---- loop 1: register window; two rounds in a row that mostly miss end it (for this and the next 7 columns) ----
+        if (skip_window > 0) --skip_window;
+        else for (int bad = 0; r < rounds && bad < 2; ++r) {
             unsigned xaddr = chunk_gate(r);
             const bool has_next = r + 1 < rounds;
+            int missed = 0;
             prefetch_round(r);
-            if (windowed) {
-                int missed = 0;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
-                    if (has_next) load_group(u);
-                    double x0, x1, x2, x3;
-                    load_x(xaddr, x0, x1, x2, x3);
-                    xaddr += 1024u;
-                    const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
-                    const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
-                    const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
-                    const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
-                    const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
-                    const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
-                    if (__all_sync(0xffffffffu, mine)) {
-                        win_add_product(w, p0, __fma_rn(a0, x0, -p0));
-                        win_add_product(w, p1, __fma_rn(a1, x1, -p1));
-                        win_add_product(w, p2, __fma_rn(a2, x2, -p2));
-                        win_add_product(w, p3, __fma_rn(a3, x3, -p3));
-                        w.cnt += 4u;
-                    } else {
-                        w = prod_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
-                        ++missed;
-                    }
+            for (int u = 0; u < U; ++u) {
+                const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
+                if (has_next) load_group(u);
+                double x0, x1, x2, x3;
+                load_x(xaddr, x0, x1, x2, x3);
+                xaddr += 1024u;
+                const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
+                const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
+                const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
+                const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
+                const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
+                const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+                if (__all_sync(0xffffffffu, mine)) {
+                    win_add_product(w, p0, __fma_rn(a0, x0, -p0));
+                    win_add_product(w, p1, __fma_rn(a1, x1, -p1));
+                    win_add_product(w, p2, __fma_rn(a2, x2, -p2));
+                    win_add_product(w, p3, __fma_rn(a3, x3, -p3));
+                    w.cnt += 4u;
+                } else {
+                    w = prod_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
+                    ++missed;
                 }
-                bad = (2 * missed > U) ? bad + 1 : 0;
-                if (bad >= 2) {                                                      // warp-uniform (the votes are)
-                    skip_window = 7;
-                    windowed = false;
-                }
-                if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) {
-                    w = win_flush_products(w, col, stride);
-                    since_norm += 4;
-                }
-                since_norm += missed * 12;
-            } else {
-                // wide-range column: every product takes the ordinary path, inlined
-                unsigned status = w.st;
+            }
+            bad = (2 * missed > U) ? bad + 1 : 0;
+            if (bad >= 2) skip_window = 7;
+            if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) {
+                w = win_flush_products(w, col, stride);
+                since_norm += 4;
+            }
+            since_norm += missed * 12;
+            if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
+                bound_column(col, stride);
+                since_norm = 0;
+            }
+        }
+        // ---- loop 2: wide-range column, every product takes the ordinary path, inlined ----
+        if (r < rounds) {
+            unsigned status = w.st;
+            for (; r < rounds; ++r) {
+                unsigned xaddr = chunk_gate(r);
+                const bool has_next = r + 1 < rounds;
+                prefetch_round(r);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
@@ -605,13 +614,13 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
                     double none[1][expansions(0)];
                     mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
                 }
-                w.st = status;
                 since_norm += 8 * U;
+                if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
+                    bound_column(col, stride);
+                    since_norm = 0;
+                }
             }
-            if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
-                bound_column(col, stride);
-                since_norm = 0;
-            }
+            w.st = status;
         }
         // rows the full rounds do not cover (fewer than 128 * (U + 1)): they lie in ONE chunk, the last
         {
