@@ -162,11 +162,13 @@ EXB_D void two_sum(double& a, double& x) {
 // this thread (!UNIFORM) holds a non-zero residual: one vote per level per four elements, taken
 // on the integer bit patterns (no FP64-pipe compare, no divergence).  Residuals come back in x[].
 template <int F, bool EE, bool UNIFORM>
-EXB_D void fpe_push4(double (&a)[F > 0 ? F : 1][expansions(F)], double (&x)[4], int first) {
+EXB_D int fpe_push4(double (&a)[F > 0 ? F : 1][expansions(F)], double (&x)[4], int first) {
     constexpr int M1 = expansions(F) - 1;
+    int walked = 0;                                        // levels visited (warp-uniform when UNIFORM)
 #pragma unroll
     for (int i = 0; i < F; ++i) {
         if (i < first) continue;
+        ++walked;
         two_sum(a[i][0], x[0]);
         two_sum(a[i][M1], x[1]);
         two_sum(a[i][0], x[2]);
@@ -183,6 +185,7 @@ EXB_D void fpe_push4(double (&a)[F > 0 ? F : 1][expansions(F)], double (&x)[4], 
             }
         }
     }
+    return walked;
 }
 
 // One summand through the levels [first, F) of expansion 0 (alignment heads, tails and strided
@@ -214,7 +217,8 @@ EXB_D int deposit_residuals(unsigned col, unsigned stride, const double (&x)[4],
 // Four ordinary inputs (any doubles) through the expansion.  No lane leaves early (the votes in
 // fpe_push4 must be reached by all lanes): Inf / NaN / |x| >= 2^988 are diverted and replaced by 0.
 template <int F, bool EE, bool UNIFORM>
-EXB_D int add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][expansions(F)], unsigned& status, double (&x)[4]) {
+EXB_D int add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][expansions(F)], unsigned& status, double (&x)[4],
+               int* walked = nullptr) {
     const unsigned h0 = (unsigned)__double2hiint(x[0]) & 0x7fffffffu, h1 = (unsigned)__double2hiint(x[1]) & 0x7fffffffu;
     const unsigned h2 = (unsigned)__double2hiint(x[2]) & 0x7fffffffu, h3 = (unsigned)__double2hiint(x[3]) & 0x7fffffffu;
     if (max(max(h0, h1), max(h2, h3)) >= (kELim << 20)) {
@@ -227,7 +231,8 @@ EXB_D int add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][expansi
             }
         }
     }
-    fpe_push4<F, EE, UNIFORM>(a, x, 0);
+    const int lv = fpe_push4<F, EE, UNIFORM>(a, x, 0);
+    if (walked) *walked += lv;
     const unsigned any = (unsigned)nonzero_bits(x[0]) | (unsigned)nonzero_bits(x[1]) | (unsigned)nonzero_bits(x[2]) |
                          (unsigned)nonzero_bits(x[3]);
     return any ? deposit_residuals(col, stride, x, status) : 0;
@@ -281,7 +286,7 @@ __device__ __noinline__ unsigned product_slow(unsigned col, unsigned stride, dou
 // exit).  F == 0: both parts are deposited directly (ExDOT.Superacc.cl:244-253).
 template <int F, bool EE, bool UNIFORM, bool P3 = UNIFORM>
 EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][expansions(F)], unsigned& status,
-                   const double (&x)[4], const double (&y)[4]) {
+                   const double (&x)[4], const double (&y)[4], int* walked = nullptr) {
     double p[4], e[4];
     unsigned worst = 0u;
 #pragma unroll
@@ -321,12 +326,13 @@ EXB_D int mul_add4(unsigned col, unsigned stride, double (&a)[F > 0 ? F : 1][exp
         return 0;
     }
     int cnt = 0;
-    fpe_push4<F, EE, UNIFORM>(a, p, 0);
+    int lv = fpe_push4<F, EE, UNIFORM>(a, p, 0);
     unsigned any = (unsigned)nonzero_bits(p[0]) | (unsigned)nonzero_bits(p[1]) | (unsigned)nonzero_bits(p[2]) |
                    (unsigned)nonzero_bits(p[3]);
     if (any) cnt += deposit_residuals(col, stride, p, status);
     constexpr int first = EE ? (F > 1 ? 1 : 0) : (F > 3 ? F - 3 : 0);
-    fpe_push4<F, EE, UNIFORM>(a, e, first);
+    lv += fpe_push4<F, EE, UNIFORM>(a, e, first);
+    if (walked) *walked += lv;
     any = (unsigned)nonzero_bits(e[0]) | (unsigned)nonzero_bits(e[1]) | (unsigned)nonzero_bits(e[2]) |
           (unsigned)nonzero_bits(e[3]);
     if (any) cnt += deposit_residuals(col, stride, e, status);
@@ -1047,6 +1053,7 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
             const bool has_next = it + 1 < iters;
             const bool direct = (F == 0) || (prm.adaptive && bypass > 0);
             int deposits = 0;
+            int walked = 0;                                 // expansion levels visited in this tile (warp-uniform)
             // Two separately unrolled tile bodies (only one is hot at a time, so each fits the
             // instruction cache): direct deposits, or the expansion walk.  Each vector slot is
             // refilled for the next tile right after it is consumed.
@@ -1094,9 +1101,9 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
                     double x[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
                     if (DOT) {
                         const double y[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-                        deposits += mul_add4<F, EE, true>(col, stride, a, status, x, y);
+                        deposits += mul_add4<F, EE, true>(col, stride, a, status, x, y, &walked);
                     } else {
-                        deposits += add4<F, EE, true>(col, stride, a, status, x);
+                        deposits += add4<F, EE, true>(col, stride, a, status, x, &walked);
                     }
                     if (has_next) {
                         va[u] = ldg256(pa + u * vstep);
@@ -1112,7 +1119,13 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
                     // ~1.5 % of the warp's summands need one, nearly every vector step pays for it and
                     // depositing everything directly is cheaper.  Back off exponentially while it lasts.
                     const int total = __reduce_add_sync(0xffffffffu, deposits);
-                    if (total * 64 >= 32 * kDepPerTile) {
+                    // Early-exit kernels [r2]: a walk that keeps going deep is slower than depositing directly although
+                    // nothing falls off the end -- every level is a vote and six dependent FP64 adds for four summands
+                    // (ExDOT fpe 8 ee on ill-conditioned products: ~8 levels per product, 3.3 TB/s, FP64 pipe 56 % busy
+                    // on latency; direct three-limb deposits run the same data at 5.3+).  More than 4 levels per ExSUM
+                    // vector / 6 per ExDOT vector (p and e together) on average over a tile counts as thrashing too.
+                    constexpr int kDeepWalk = (DOT ? 6 : 4) * U;
+                    if (total * 64 >= 32 * kDepPerTile || (EE && walked > kDeepWalk)) {
                         bypass = backoff;
                         backoff = min(backoff * 16, kBypassMax);   // a second thrashing probe in a row: stay away for long
                     } else {
