@@ -720,9 +720,9 @@ __device__ __noinline__ void block_merge_and_close(const ReduceParams& prm, cons
         atomicMin(&block_status[1], row_lo);
         atomicMax(&block_status[2], row_hi);
     }
-    if (tid < (unsigned)kLimbs) {
-        block_lo[tid] = 0;
-        block_hi[tid] = 0;
+    for (unsigned j = tid; j < (unsigned)kLimbs; j += T) {       // (T may be as small as 32)
+        block_lo[j] = 0;
+        block_hi[j] = 0;
     }
     __syncthreads();                                       // row range and block sums initialised; all columns final
     if (status) {

@@ -191,6 +191,16 @@ def test_result_independent_of_launch_shape(gpu, oracle):
                 for fpe, ee in [(0, False), (3, False), (8, True)]:
                     v, l = gpu.exsum(n, d, 1, 0, fpe, ee, want_limbs=True)
                     assert same_double(v, v0) and (l == l0).all(), (T, blocks, fpe, ee)
+        # hand-set small CTAs on SHORT vectors: the touched-row tracking path with fewer threads than limbs
+        for n2 in (100, 5000, 70001):
+            w0, wl0 = oracle.exsum(a[:n2], fpe=0)
+            for T in (32, 64, 96):
+                for blocks in (1, 3):
+                    gpu.set_option("block_threads", T)
+                    gpu.set_option("blocks", blocks)
+                    for fpe, ee in [(0, False), (4, False), (8, True)]:
+                        v, l = gpu.exsum(n2, d, 1, 0, fpe, ee, want_limbs=True)
+                        assert same_double(v, w0) and (l == wl0).all(), (n2, T, blocks, fpe, ee)
     finally:
         gpu.set_option("auto_shape", 1)
 
