@@ -242,6 +242,7 @@ struct exblas_b200_handle_s {
     int64_t opt_gemv_parts = 0;
     int64_t opt_gemv_t_shape = 2;
     int64_t opt_gemv_n_shape = 1;
+    int64_t opt_reduce_prefetch = 0;        // expansion kernel: L2 bulk-prefetch distance in tiles (0 = off)
     int64_t opt_gemv_prefetch = 2;          // ExGEMV window kernels: L2 bulk-prefetch distance in rounds (0 = off)
     int64_t opt_window = 2;                 // register window in the superaccumulator-only kernels (performance only)
     bool opt_shape_fixed = false;           // "block_threads" / "blocks" were set by hand: no size-dependent launch shape
@@ -380,6 +381,7 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     const int64_t work = p.nvec > 0 ? p.nvec : (n + 7) / 8;      // 256-bit vectors (scalar path: groups of 8 loads)
     p.peer_timeout_ns = (unsigned long long)h->opt_peer_timeout_ms * 1000000ull;
     p.phase = h->d_phase;
+    p.l2_prefetch = (int)h->opt_reduce_prefetch;
     if (!h->opt_shape_fixed && n <= h->opt_solo_max && p.fresh && finalize) {
         // latency regime: the small single-CTA kernel (every fpe value: fpe never changes the result)
         const int64_t per_thread4 = p.nvec > 0 ? (p.nvec + 3) / 4 : (n + 3) / 4;
@@ -1047,6 +1049,9 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "gemv_t_shape")) {
         if (value < 0 || value > 3) return EXBLAS_B200_EINVAL;
         h->opt_gemv_t_shape = value;
+    } else if (!strcmp(name, "reduce_prefetch")) {
+        if (value < 0 || value > 16) return EXBLAS_B200_EINVAL;
+        h->opt_reduce_prefetch = value;
     } else if (!strcmp(name, "gemv_prefetch")) {
         if (value < 0 || value > 16) return EXBLAS_B200_EINVAL;
         h->opt_gemv_prefetch = value;

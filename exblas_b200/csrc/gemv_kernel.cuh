@@ -43,11 +43,6 @@ struct GemvParams {
     int l2_prefetch;        // window kernels: bulk L2 prefetch distance in rounds (0 = off; needs A 16-byte aligned, lda even)
 };
 
-// TMA-engine prefetch of a contiguous run of global memory into L2 (no destination in shared memory, no completion to
-// wait for): SASS UBLKPF.  `bytes` must be a multiple of 16 and `p` 16-byte aligned.
-EXB_D void bulk_prefetch_l2(const void* p, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 
 EXB_D Vec4 ldg256_cached(const double* p) {     // through L1: x is re-read by every warp of the CTA
     Vec4 r;

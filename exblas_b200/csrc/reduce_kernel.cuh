@@ -88,6 +88,7 @@ struct ReduceParams {
     int nranks, rank;
     unsigned long long epoch;            // identifies this collective reduction (same on every rank, >= 1)
     unsigned long long peer_timeout_ns;  // give up waiting for a peer after this long (0 = wait for ever)
+    int l2_prefetch;                     // expansion kernel: bulk L2 prefetch distance in tiles (0 = off; performance only)
     unsigned long long* phase;           // optional [gridDim.x][kPhaseSlots] globaltimer stamps (nullptr = off)
 };
 
@@ -97,6 +98,12 @@ EXB_D Vec4 ldg256(const double* p) {
                  : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
                  : "l"(p));
     return r;
+}
+
+// TMA-engine prefetch of a contiguous run of global memory into L2 (no destination in shared memory, no completion to
+// wait for): SASS UBLKPF.  `bytes` must be a multiple of 16 and `p` 16-byte aligned.
+EXB_D void bulk_prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 EXB_D double ldg64(const double* p) {
@@ -1019,6 +1026,16 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
         }
         // clear the (thread-private: no barrier needed) column while the first loads are in flight
         for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
+        // TMA-engine L2 prefetch of whole tiles (one UBLKPF per tile and stream, thread 0): D tiles ahead of the loads
+        const int pfd = prm.l2_prefetch;
+        const double* pfa = prm.a + prm.head + (long long)blockIdx.x * TILE;
+        const double* pfb = DOT ? prm.b + prm.head + (long long)blockIdx.x * TILE : nullptr;
+        if (pfd > 0 && tid == 0) {
+            for (int d = 1; d <= pfd && (unsigned)d < iters; ++d) {
+                bulk_prefetch_l2(pfa + (long long)d * tile_step, (unsigned)(TILE * 8));
+                if (DOT) bulk_prefetch_l2(pfb + (long long)d * tile_step, (unsigned)(TILE * 8));
+            }
+        }
         int bypass = 0, backoff = kBypassTiles;
         // The first probe of the expansion is skipped when the exponents of the first tile alone span more than an
         // F-level expansion can hold (log-uniform 2^+-332 against 53 F bits): walking a thrashing tile costs ~10 direct
@@ -1051,6 +1068,10 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
             pa += tile_step;
             if (DOT) pb += tile_step;
             const bool has_next = it + 1 < iters;
+            if (pfd > 0 && tid == 0 && it + 1u + (unsigned)pfd < iters) {
+                bulk_prefetch_l2(pfa + (long long)(it + 1u + (unsigned)pfd) * tile_step, (unsigned)(TILE * 8));
+                if (DOT) bulk_prefetch_l2(pfb + (long long)(it + 1u + (unsigned)pfd) * tile_step, (unsigned)(TILE * 8));
+            }
             const bool direct = (F == 0) || (prm.adaptive && bypass > 0);
             int deposits = 0;
             int walked = 0;                                 // expansion levels visited in this tile (warp-uniform)
