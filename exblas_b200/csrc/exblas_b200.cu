@@ -243,6 +243,7 @@ struct exblas_b200_handle_s {
     int64_t opt_gemv_t_shape = 2;
     int64_t opt_gemv_n_shape = 1;
     int64_t opt_reduce_prefetch = 0;        // expansion kernel: L2 bulk-prefetch distance in tiles (0 = off)
+    int64_t opt_gemv_tma = 1;               // ExGEMV 'T': stage x with TMA bulk copies (0 = plain copies by a warp; for A/B and tests)
     int64_t opt_gemv_prefetch = 2;          // ExGEMV window kernels: L2 bulk-prefetch distance in rounds (0 = off)
     int64_t opt_window = 2;                 // register window in the superaccumulator-only kernels (performance only)
     bool opt_shape_fixed = false;           // "block_threads" / "blocks" were set by hand: no size-dependent launch shape
@@ -666,7 +667,7 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     // 'T' with alpha == 1 and columns long enough to amortise the per-output warp merge: one warp per
     // output, register windows, no scratch and no second kernel (exgemv_t_win_kernel).  Every fpe value
     // takes it -- fpe only selects HOW the exact sum is accumulated, never the result.
-    if (transposed && alpha == 1.0 && h->opt_window && n >= 256) {
+    if (transposed && alpha == 1.0 && h->opt_window && n >= 256 && n < (1ll << 31) - 65536 && m < (1ll << 31)) {   // (32-bit row / set counters)
         GemvParams p;
         memset(&p, 0, sizeof(p));
         p.a = a;
@@ -683,6 +684,7 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
         p.ws = h->d_ws;
         p.round_mode = round_mode;
         p.l2_prefetch = (((uintptr_t)a % 16) == 0 && (rs % 2) == 0) ? (int)h->opt_gemv_prefetch : 0;
+        p.x_vec_ok = (incx == 1 && ((uintptr_t)x % 16) == 0 && h->opt_gemv_tma) ? 1 : 0;   // x chunks by cp.async.bulk (else copied by a warp)
         // launch shapes (option "gemv_t_shape"): threads x groups of 4 rows in flight per lane x rows of x per buffer
         struct TShape { int T, chunk; gemv_fn fn; };
         static const TShape shapes[] = {
@@ -695,7 +697,7 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
         const int T = sh.T, nwarps = T / 32, chunk = sh.chunk;
         const int64_t nsets = (m + nwarps - 1) / nwarps;
         const unsigned grid = (unsigned)(nsets < h->num_sms ? nsets : h->num_sms);
-        const size_t smem = ((size_t)T * kLimbs + 2 * (size_t)chunk + 40 * (size_t)nwarps) * sizeof(long long);
+        const size_t smem = ((size_t)T * kLimbs + 2 * (size_t)chunk + 40 * (size_t)nwarps) * sizeof(long long) + 32;   // + the x pipeline's mbarriers / counters
         gemv_fn fn = sh.fn;
         CK(allow_big_smem((const void*)fn, h->device));
         void* args[] = {(void*)&p};
@@ -1049,6 +1051,8 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "gemv_t_shape")) {
         if (value < 0 || value > 3) return EXBLAS_B200_EINVAL;
         h->opt_gemv_t_shape = value;
+    } else if (!strcmp(name, "gemv_tma")) {
+        h->opt_gemv_tma = value ? 1 : 0;
     } else if (!strcmp(name, "reduce_prefetch")) {
         if (value < 0 || value > 16) return EXBLAS_B200_EINVAL;
         h->opt_reduce_prefetch = value;

@@ -323,7 +323,6 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
-            if (has_next) load_group(u);
             double x0, x1, x2, x3;
             lds128(xaddr, x0, x1);
             lds128(xaddr + 16u, x2, x3);
@@ -344,6 +343,9 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
                 w = prod_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
                 ++missed;
             }
+            // the slot is refilled AFTER its values are dead: a predicated load issued while they were still needed made
+            // the compiler copy all eight registers first (8 moves per group, ~8 % of the loop's instructions)
+            if (has_next) load_group(u);
         }
         bad = (2 * missed > U) ? bad + 1 : 0;                // warp-uniform (the votes are)
         if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) {
@@ -458,145 +460,251 @@ __device__ __noinline__ void gemv_t_store(const long long* wl, unsigned st, doub
 
 constexpr int kGemvTChunk = EXB_TCHUNK;   // rows of x staged per buffer
 
+// The out-of-line halves of exgemv_t_win_kernel's window loop.  Besides the work itself they keep the count of ordinary
+// deposits since the column was last bounded -- in bits 16.. of w.st (the status flags live in bits 0..5 and are only
+// ever OR-ed in) -- and bound the column when it is due, so that the streaming loop carries no counter for it.
+constexpr unsigned kTDepUnit = 1u << 16;
+constexpr unsigned kTDepLimit = (unsigned)(kMaxDepositsPerNormalize - 160);   // room for a slow group, a flush and the <= 36-row remainder
+EXB_D Window t_dep_note(Window w, unsigned col, unsigned stride, unsigned deposits) {
+    w.st += deposits * kTDepUnit;
+    if ((w.st >> 16) > kTDepLimit) {
+        bound_column(col, stride);
+        w.st &= 0xffffu;
+    }
+    return w;
+}
+__device__ __noinline__ Window t_slow_group(Window w, unsigned col, unsigned stride, double a0, double a1, double a2, double a3,
+                                            double x0, double x1, double x2, double x3, bool mine) {
+    w = prod_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
+    return t_dep_note(w, col, stride, 12u);                  // <= 8 deposits + a 4-deposit drain
+}
+__device__ __noinline__ Window t_flush(Window w, unsigned col, unsigned stride) {
+    w = win_flush_products(w, col, stride);
+    return t_dep_note(w, col, stride, 4u);
+}
+
+// ---- x pipeline of exgemv_t_win_kernel: TMA bulk copies + mbarriers, no CTA-wide barrier ----------------------------
+// All warps of a CTA walk the same rows of their columns, so x is staged per CTA, kGemvTChunk rows at a time, in two
+// buffers.  Chunks are numbered g = 0, 1, 2, ... through the whole life of the CTA (x is the same for every set of
+// columns, so chunk g is rows (g mod nchunks) * CH ... of x) and live in buffer g & 1:
+//   * a warp about to read chunk g waits on the buffer's "full" mbarrier (phase (g >> 1) & 1);
+//   * a warp that has finished chunk g counts itself out on the buffer's counter; the LAST warp out resets the counter and
+//     issues chunk g + 2 into the buffer: one cp.async.bulk (TMA engine, SASS UBLKCP) that completes on the mbarrier --
+//     or, when x is strided or not 16-byte aligned, a copy by that warp followed by an ordinary arrive.
+// Nobody waits for a slower warp unless it runs a whole chunk ahead of it (round 1 / early round 2: cp.async by all
+// threads + one bar.sync per chunk, 10 % of all warp stall cycles).
+EXB_D void mbar_init(unsigned addr, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); }
+EXB_D void mbar_arrive(unsigned addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+EXB_D void mbar_expect_tx(unsigned addr, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+EXB_D void mbar_wait(unsigned addr, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "EXB_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra EXB_MBAR_DONE;\n"
+        "bra EXB_MBAR_WAIT;\n"
+        "EXB_MBAR_DONE:\n"
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+EXB_D void bulk_copy_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(mbar) : "memory");
+}
+
+struct TPipe {                 // addresses in the shared window
+    unsigned xs_base;          // 2 x CH doubles
+    unsigned ctl;              // full[0], full[1] (mbarriers, 8 B each), out[0], out[1] (counters, 4 B each)
+};
+
+// Whole warp: bring chunk g of the CTA's sequence into buffer g & 1 (out of line: once per chunk and CTA).
+template <int CH>
+__device__ __noinline__ void t_issue_chunk(const TPipe tp, const double* x, long long incx, int nrows, int nchunks, unsigned g,
+                                           int bulk_ok) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned b = g & 1u;
+    const int chunk = (int)(g % (unsigned)nchunks);
+    const int r0 = chunk * CH;
+    const int cnt = nrows - r0 < CH ? nrows - r0 : CH;
+    const unsigned dst = tp.xs_base + b * (CH * 8u);
+    const unsigned full = tp.ctl + 8u * b;
+    const int nb = bulk_ok ? (cnt & ~1) : 0;                           // 16-byte granules through the TMA engine
+    for (int k0 = nb + (int)lane; k0 < cnt; k0 += 256) {               // (strided / unaligned x, or the odd last row) eight loads in flight per lane
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = k0 + 32 * i < cnt ? ldg64(x + incx * (long long)(r0 + k0 + 32 * i)) : 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (k0 + 32 * i < cnt) sts64(dst + 8u * (unsigned)(k0 + 32 * i), (unsigned long long)__double_as_longlong(v[i]));
+    }
+    __syncwarp();
+    if (lane == 0u) {
+        if (nb > 0) {
+            mbar_expect_tx(full, (unsigned)nb * 8u);                   // the arrival + the bytes the copy will deliver
+            bulk_copy_g2s(dst, x + r0, (unsigned)nb * 8u, full);
+        } else {
+            mbar_arrive(full);                                         // release: the warp's stores above are ordered before it
+        }
+    }
+}
+
 template <int U, int MAXT, int kGemvTChunk>
 __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams prm) {
     // (A variant in which lane l reads rows 4l .. 4l+3 with one 256-bit load was measured slower: its
     // x reads, 32 bytes apart per lane, conflict in shared memory, and the wider requests bought nothing.)
-    constexpr bool VEC = false;
-    // here prm.m = number of outputs (columns of A), prm.n = rows summed per output, prm.rs = lda, prm.cs = 1
+    // here prm.m = number of outputs (columns of A), prm.n = rows summed per output (< 2^31, the host checks),
+    // prm.rs = lda, prm.cs = 1
+    //
+    // Register discipline [r2]: at 512 threads a thread has 128 registers, 32 of them hold A values in flight and ~45 the
+    // window and its split.  Everything the streaming loop does not need every round lives elsewhere -- the deposit count
+    // in w.st (above), the "skip the window" count in the warp's shared-memory slot, 32-bit round counters, the prefetch
+    // address derived from the load pointer.
     extern __shared__ long long smem[];
     const unsigned T = blockDim.x;                                                   // <= MAXT
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = T >> 5;
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
     constexpr unsigned stride = 8u * MAXT;                                           // compile-time limb stride
     const unsigned col = smem_base + 8u * tid;
 #pragma unroll
     for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
-    const unsigned xs_base = smem_base + stride * (unsigned)kLimbs;                  // 2 x kGemvTChunk doubles
-    long long* wl = smem + (size_t)kLimbs * MAXT + 2 * kGemvTChunk + (size_t)warp * 40;   // this warp's 39 summed limbs
+    constexpr unsigned kXsOff = stride * (unsigned)kLimbs;                           // 2 x kGemvTChunk doubles
+    constexpr unsigned kWlOff = kXsOff + 16u * kGemvTChunk;                          // per warp: 39 summed limbs + the skip count
+    constexpr unsigned kCtlOff = kWlOff + (MAXT / 32u) * 320u;                       // the pipeline's mbarriers and counters
+    const unsigned wl_addr = smem_base + kWlOff + (tid >> 5) * 320u;
+    TPipe tp;
+    tp.xs_base = smem_base + kXsOff;
+    tp.ctl = smem_base + kCtlOff;
 
-    const long long nrows = prm.n, nout = prm.m;
-    const long long nsets = (nout + nwarps - 1) / nwarps;
-    const int nchunks = (int)((nrows + kGemvTChunk - 1) / kGemvTChunk);
-    const long long full_groups = nrows / 128;                                       // groups of 4 rows per lane, all rows valid
+    const int nrows = (int)prm.n;
+    const int nwarps = (int)(T >> 5);
+    const int nsets = (int)((prm.m + nwarps - 1) / nwarps);
+    const int nchunks = (nrows + kGemvTChunk - 1) / kGemvTChunk;
+    const int rounds = nrows / (128 * U);                                            // rounds of U groups of 4 rows per lane, all rows valid
+    constexpr int RPC = kGemvTChunk / (128 * U);                                     // rounds per chunk of x
+    static_assert(RPC * 128 * U == kGemvTChunk && (RPC & (RPC - 1)) == 0, "a chunk of x holds a power of two of whole rounds");
+    const int my_sets = (int)blockIdx.x < nsets ? (nsets - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const unsigned gtotal = (unsigned)my_sets * (unsigned)nchunks;                   // chunks this CTA will consume
 
-    auto stage = [&](int chunk) {                                                    // x[chunk] -> buffer chunk & 1 (zero padded)
-        const unsigned dst0 = xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u);
-        const long long r0 = (long long)chunk * kGemvTChunk;
-        for (int k = (int)tid; k < kGemvTChunk; k += (int)T) {
-            const long long r = r0 + k;
-            if (r < nrows) cp_async8(dst0 + 8u * (unsigned)k, prm.x + prm.incx * r);
-            else sts64(dst0 + 8u * (unsigned)k, 0ull);
+    if (lane == 0u) sts64(wl_addr + 312u, 0ull);
+    if (tid == 0u) {
+        mbar_init(tp.ctl, 1u);
+        mbar_init(tp.ctl + 8u, 1u);
+        sts64(tp.ctl + 16u, 0ull);                                                   // both counters
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 32u) {                                                                 // warp 0 starts the pipeline
+        if (gtotal > 0u) t_issue_chunk<kGemvTChunk>(tp, prm.x, prm.incx, nrows, nchunks, 0u, prm.x_vec_ok);
+        if (gtotal > 1u) t_issue_chunk<kGemvTChunk>(tp, prm.x, prm.incx, nrows, nchunks, 1u, prm.x_vec_ok);
+    }
+    // chunk g: wait until it is resident; returns the shared address of this lane's x for the first round of the chunk
+    auto acquire = [&](unsigned g) -> unsigned {
+        mbar_wait(tp.ctl + 8u * (g & 1u), (g >> 1) & 1u);
+        return tp.xs_base + (g & 1u) * (kGemvTChunk * 8u) + 8u * lane;
+    };
+    // chunk g: this warp is done with it; the last warp out refills the buffer with chunk g + 2
+    auto release = [&](unsigned g) {
+        __syncwarp();
+        unsigned old = 0u;
+        __threadfence_block();
+        if (lane == 0u) old = atomicAdd((unsigned*)((char*)smem + kCtlOff + 16u + 4u * (g & 1u)), 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == (unsigned)nwarps - 1u) {
+            if (lane == 0u) *(volatile unsigned*)((char*)smem + kCtlOff + 16u + 4u * (g & 1u)) = 0u;
+            if (g + 2u < gtotal) t_issue_chunk<kGemvTChunk>(tp, prm.x, prm.incx, nrows, nchunks, g + 2u, prm.x_vec_ok);
         }
     };
 
     Window w;
     win_reset(w);
-    int skip_window = 0;                                                             // columns left to run without the window
-    for (long long set = blockIdx.x; set < nsets; set += gridDim.x) {
-        const long long jraw = set * nwarps + warp;
-        const bool valid = jraw < nout;
-        const long long j = valid ? jraw : nout - 1;                                 // spare warps redo the last column (they must meet the barriers)
-        const double* qa = prm.a + j * prm.rs + (VEC ? 4u * lane : lane);            // this lane's first row of column j
+    unsigned gbase = 0u;                                                             // sequence number of chunk 0 of the current set
+    for (int set = (int)blockIdx.x; set < nsets; set += (int)gridDim.x, gbase += (unsigned)nchunks) {
+        const double* qa;                                                            // this lane's next group of 4 rows
+        {
+            const long long jraw = (long long)set * nwarps + (tid >> 5);
+            const long long j = jraw < prm.m ? jraw : prm.m - 1;                     // spare warps redo the last column (they take part in the x pipeline)
+            qa = prm.a + j * prm.rs + lane;
+        }
         double va[U][4];
         auto load_group = [&](int u) {
-            if (VEC) {
-                const Vec4 v = ldg256(qa);
-                va[u][0] = v.x; va[u][1] = v.y; va[u][2] = v.z; va[u][3] = v.w;
-            } else {
-                va[u][0] = ldg64(qa);
-                va[u][1] = ldg64(qa + 32);
-                va[u][2] = ldg64(qa + 64);
-                va[u][3] = ldg64(qa + 96);
-            }
+            va[u][0] = ldg64(qa);
+            va[u][1] = ldg64(qa + 32);
+            va[u][2] = ldg64(qa + 64);
+            va[u][3] = ldg64(qa + 96);
             qa += 128;
         };
         auto load_x = [&](unsigned xaddr, double& x0, double& x1, double& x2, double& x3) {
-            if (VEC) {
-                lds128(xaddr, x0, x1);
-                lds128(xaddr + 16u, x2, x3);
-            } else {
-                x0 = lds_f64(xaddr); x1 = lds_f64(xaddr + 256u); x2 = lds_f64(xaddr + 512u); x3 = lds_f64(xaddr + 768u);
-            }
+            x0 = lds_f64(xaddr); x1 = lds_f64(xaddr + 256u); x2 = lds_f64(xaddr + 512u); x3 = lds_f64(xaddr + 768u);
         };
-        const long long rounds = full_groups / U;
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (rounds > 0) load_group(u);
-        // L2 prefetch (TMA engine, UBLKPF): lane 0 asks for the 128 U rows of this warp's column that round r + D will read
-        const double* pf_col = prm.a + j * prm.rs;
+        // L2 prefetch (TMA engine, UBLKPF): at the top of round r the load pointer of lane 0 stands at the first row of round
+        // r + 1, so the 128 U rows that round r + D will read start (D - 1) rounds further on
         const int pf_dist = prm.l2_prefetch;
-        auto prefetch_round = [&](long long rr) {
-            if (pf_dist > 0 && lane == 0u && rr + pf_dist < rounds) bulk_prefetch_l2(pf_col + (rr + pf_dist) * (128 * U), 128u * U * 8u);
+        auto prefetch_round = [&](int r) {
+            if (pf_dist > 0 && lane == 0u && r + pf_dist < rounds) bulk_prefetch_l2(qa + (pf_dist - 1) * (128 * U), 128u * U * 8u);
         };
-        __syncthreads();                                                             // previous set's readers of both x buffers are done
-        stage(0);
-        int since_norm = 0;
-        constexpr int RPC = kGemvTChunk / (128 * U);                                 // rounds per chunk of x
-        static_assert(RPC * 128 * U == kGemvTChunk, "a chunk of x must hold whole rounds");
-        auto chunk_gate = [&](long long r) -> unsigned {                             // returns the shared address of this lane's x for round r
-            const int chunk = (int)(r / RPC);
-            if (r % RPC == 0) {
-                cp_async_wait_all();
-                bar_sync_named(T);                                                   // chunk resident; buffer (chunk + 1) & 1 is free
-                if (chunk + 1 < nchunks) stage(chunk + 1);
-            }
-            return xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u) + (unsigned)(r % RPC) * (128u * U * 8u) + (VEC ? 32u : 8u) * lane;
+        // top of round r: every RPC rounds hand the finished chunk back and pick up the next one
+        auto chunk_gate = [&](int r) -> unsigned {
+            const unsigned g = gbase + (unsigned)(r / RPC);
+            if (r > 0) release(g - 1u);
+            return acquire(g);
         };
-        // Two loops (window mode, then -- for a warp whose column turns out wide -- plain deposits); each calls chunk_gate
-        // once per round.  Which loop a warp is in depends on its own data, so the CTA-wide hand-over of the x chunks is a
-        // NAMED barrier with an explicit thread count (bar.sync 1, T): PTX pairs arrivals by barrier id whatever code path
-        // they come from, which __syncthreads() in warp-divergent control flow does not promise.  (One merged loop with a
-        // single call site was measured 6 % slower: both bodies in one loop cost the window path registers.)
-        long long r = 0;
-        // ---- loop 1: register window; two rounds in a row that mostly miss end it (for this and the next 7 columns) ----
-        if (skip_window > 0) --skip_window;
-        else for (int bad = 0; r < rounds && bad < 2; ++r) {
-            unsigned xaddr = chunk_gate(r);
-            const bool has_next = r + 1 < rounds;
-            int missed = 0;
-            prefetch_round(r);
+        int r = 0;
+        unsigned xaddr = 0u;
+        // ---- loop 1: register window; a warp whose groups keep missing leaves it (for this and the next 7 columns) ----
+        const unsigned skip_window = (unsigned)lds64(wl_addr + 312u);
+        if (skip_window > 0u) {
+            __syncwarp();
+            if (lane == 0u) sts64(wl_addr + 312u, (unsigned long long)(skip_window - 1u));
+        } else {
+            // leaky bucket, warp-uniform (the votes are): +2 per group that missed, -U per round; two rounds in a row
+            // that miss throughout end the loop
+            for (int score = 0; r < rounds && score <= U; ++r) {
+                if ((r & (RPC - 1)) == 0) xaddr = chunk_gate(r);
+                const bool has_next = r + 1 < rounds;
+                prefetch_round(r);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
-                if (has_next) load_group(u);
-                double x0, x1, x2, x3;
-                load_x(xaddr, x0, x1, x2, x3);
-                xaddr += 1024u;
-                const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
-                const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
-                const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
-                const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
-                const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
-                const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
-                if (__all_sync(0xffffffffu, mine)) {
-                    win_add_product(w, p0, __fma_rn(a0, x0, -p0));
-                    win_add_product(w, p1, __fma_rn(a1, x1, -p1));
-                    win_add_product(w, p2, __fma_rn(a2, x2, -p2));
-                    win_add_product(w, p3, __fma_rn(a3, x3, -p3));
-                    w.cnt += 4u;
-                } else {
-                    w = prod_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine, true);
-                    ++missed;
+                for (int u = 0; u < U; ++u) {
+                    const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
+                    double x0, x1, x2, x3;
+                    load_x(xaddr, x0, x1, x2, x3);
+                    xaddr += 1024u;
+                    const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
+                    const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
+                    const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
+                    const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
+                    const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
+                    const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+                    if (__all_sync(0xffffffffu, mine)) {
+                        win_add_product(w, p0, __fma_rn(a0, x0, -p0));
+                        win_add_product(w, p1, __fma_rn(a1, x1, -p1));
+                        win_add_product(w, p2, __fma_rn(a2, x2, -p2));
+                        win_add_product(w, p3, __fma_rn(a3, x3, -p3));
+                        w.cnt += 4u;
+                    } else {
+                        w = t_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine);
+                        score += 2;
+                    }
+                    if (has_next) load_group(u);                                     // after the slot's values are dead (see exgemv_n_win_kernel)
                 }
+                score = max(score - U, 0);
+                if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) w = t_flush(w, col, stride);
             }
-            bad = (2 * missed > U) ? bad + 1 : 0;
-            if (bad >= 2) skip_window = 7;
-            if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) {
-                w = win_flush_products(w, col, stride);
-                since_norm += 4;
-            }
-            since_norm += missed * 12;
-            if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
-                bound_column(col, stride);
-                since_norm = 0;
+            if (r < rounds) {
+                __syncwarp();
+                if (lane == 0u) sts64(wl_addr + 312u, 7ull);
             }
         }
         // ---- loop 2: wide-range column, every product takes the ordinary path, inlined ----
         if (r < rounds) {
-            unsigned status = w.st;
+            unsigned status = w.st & 0xffffu;
+            int since_norm = (int)(w.st >> 16);
             for (; r < rounds; ++r) {
-                unsigned xaddr = chunk_gate(r);
+                if ((r & (RPC - 1)) == 0) xaddr = chunk_gate(r);
                 const bool has_next = r + 1 < rounds;
                 prefetch_round(r);
 #pragma unroll
@@ -610,37 +718,41 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
                     mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
                 }
                 since_norm += 8 * U;
-                if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
+                if (since_norm > (int)kTDepLimit - 8 * U) {
                     bound_column(col, stride);
                     since_norm = 0;
                 }
             }
-            w.st = status;
+            w.st = status | ((unsigned)since_norm << 16);
         }
-        // rows the full rounds do not cover (fewer than 128 * (U + 1)): they lie in ONE chunk, the last
+        // rows the full rounds do not cover (fewer than 128 U): they lie in ONE chunk, the last -- which is either the
+        // chunk the last round was in or the one after it
         {
-            const long long r0 = rounds * U * 128;
-            const int synced = rounds > 0 ? (int)((rounds - 1) / RPC) + 1 : 0;       // chunks whose barrier has been passed
+            const int r0 = rounds * U * 128;
+            int cur = rounds > 0 ? (rounds - 1) / RPC : -1;                          // chunk this warp holds
             if (r0 < nrows) {
-                const int chunk = (int)(r0 / kGemvTChunk);
-                if (chunk >= synced) {
-                    cp_async_wait_all();
-                    __syncthreads();
+                const int chunk = r0 / kGemvTChunk;
+                if (chunk > cur) {
+                    if (cur >= 0) release(gbase + (unsigned)cur);
+                    (void)acquire(gbase + (unsigned)chunk);
+                    cur = chunk;
                 }
-                unsigned status = w.st;
+                unsigned status = w.st;                                              // (the count in bits 16.. rides along untouched)
                 double none[1][expansions(0)];
-                const unsigned xb = xs_base + (unsigned)(chunk & 1) * (kGemvTChunk * 8u);
-                for (long long rr = r0 + lane; rr < nrows; rr += 32) {               // <= 36 rows per lane
-                    const double xv = lds_f64(xb + 8u * (unsigned)(rr - (long long)chunk * kGemvTChunk));
-                    mul_add1<0, false>(col, stride, none, status, prm.a[j * prm.rs + rr], xv);
+                const unsigned xb = tp.xs_base + ((gbase + (unsigned)chunk) & 1u) * (kGemvTChunk * 8u);
+                const double* ra = qa;                                               // U * rounds groups have been loaded: this lane's row r0 + lane
+                for (int rr = r0 + (int)lane; rr < nrows; rr += 32, ra += 32) {      // < 4 U rows per lane
+                    const double xv = lds_f64(xb + 8u * (unsigned)(rr - chunk * kGemvTChunk));
+                    mul_add1<0, false>(col, stride, none, status, ra[0], xv);
                 }
                 w.st = status;
             }
+            release(gbase + (unsigned)cur);                                          // nrows >= 1: cur is the last chunk, nchunks - 1
         }
         // ---- end of the column: drain, warp-sum the 32 private columns, round, store ----
         w = win_flush_products(w, col, stride);
         bound_column(col, stride);
-        const unsigned st_all = __reduce_or_sync(0xffffffffu, w.st);
+        const unsigned st_all = __reduce_or_sync(0xffffffffu, w.st & 0xffffu);
         w.st = 0u;
         for (int jl = 0; jl < kLimbs; ++jl) {
             const unsigned addr = col + jl * stride;
@@ -650,10 +762,15 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // 32 x (2^52 + 2^11) < 2^58
             }
-            if (lane == 0) wl[jl] = v;
+            if (lane == 0) sts64(wl_addr + 8u * (unsigned)jl, (unsigned long long)v);
         }
         __syncwarp();
-        if (lane == 0 && valid) gemv_t_store(wl, st_all, prm.y + jraw * prm.incy, prm.beta, prm.round_mode, &prm.ws->status);
+        {
+            const long long jraw = (long long)set * nwarps + (tid >> 5);
+            if (lane == 0 && jraw < prm.m)
+                gemv_t_store(smem + (kWlOff >> 3) + (size_t)(tid >> 5) * 40, st_all, prm.y + jraw * prm.incy, prm.beta, prm.round_mode,
+                             &prm.ws->status);
+        }
         __syncwarp();
     }
 }

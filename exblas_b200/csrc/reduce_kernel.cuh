@@ -980,6 +980,31 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
     block_merge_and_close(prm, stride, smem_base, T, tid, status, solo, block_lo, block_hi, block_status, row_lo, row_hi);
 }
 
+// True when the exponents of the tile a warp holds in registers span more than an F-level expansion can hold (53 F bits
+// plus slack): such a tile is not worth walking.  Warp-uniform.
+template <int F, bool DOT, int U>
+EXB_D bool tile_too_wide(const Vec4 (&va)[U], const Vec4 (&vb)[DOT ? U : 1]) {
+    unsigned emax = 0u, emin = 0xfffu;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const double xs[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+        const double ys[4] = {vb[DOT ? u : 0].x, vb[DOT ? u : 0].y, vb[DOT ? u : 0].z, vb[DOT ? u : 0].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned e = ((unsigned)__double2hiint(xs[k]) >> 20) & 0x7ffu;
+            if (DOT) {
+                const unsigned eb = ((unsigned)__double2hiint(ys[k]) >> 20) & 0x7ffu;
+                e = (e && eb) ? e + eb : 0u;                 // exponent of the product (+ 1023), 0 for zeros
+            }
+            emax = max(emax, e);
+            emin = min(emin, e ? e : 0xfffu);
+        }
+    }
+    emax = __reduce_max_sync(kFullWarp, emax);
+    emin = __reduce_min_sync(kFullWarp, emin);
+    return emax > emin && emax - emin > 53u * F + 64u;
+}
+
 // (Measured and rejected, round 1: moving the thrash bypass or the expansion walk of THIS kernel into out-of-line
 // functions, as exblas_reduce0_kernel does with its window loop.  The expansion walk contains calls (deposits of
 // residuals), and a function that is itself called and calls on spills its prefetch slots: 1.9 instead of
@@ -1040,29 +1065,9 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
         // The first probe of the expansion is skipped when the exponents of the first tile alone span more than an
         // F-level expansion can hold (log-uniform 2^+-332 against 53 F bits): walking a thrashing tile costs ~10 direct
         // tiles, which vectors of 2^22..2^26 elements never amortise.  Later probes (after a bypass period) are real.
-        if (F > 0 && prm.adaptive) {
-            unsigned emax = 0u, emin = 0xfffu;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double xs[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
-                const double ys[4] = {vb[DOT ? u : 0].x, vb[DOT ? u : 0].y, vb[DOT ? u : 0].z, vb[DOT ? u : 0].w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    unsigned e = ((unsigned)__double2hiint(xs[k]) >> 20) & 0x7ffu;
-                    if (DOT) {
-                        const unsigned eb = ((unsigned)__double2hiint(ys[k]) >> 20) & 0x7ffu;
-                        e = (e && eb) ? e + eb : 0u;                 // exponent of the product (+ 1023), 0 for zeros
-                    }
-                    emax = max(emax, e);
-                    emin = min(emin, e ? e : 0xfffu);
-                }
-            }
-            emax = __reduce_max_sync(kFullWarp, emax);
-            emin = __reduce_min_sync(kFullWarp, emin);
-            if (emax > emin && emax - emin > 53u * F + 64u) {
-                bypass = backoff;
-                backoff = min(backoff * 16, kBypassMax);
-            }
+        if (F > 0 && prm.adaptive && tile_too_wide<F, DOT, U>(va, vb)) {
+            bypass = backoff;
+            backoff = min(backoff * 16, kBypassMax);
         }
         for (unsigned it = 0; it < iters; ++it) {
             pa += tile_step;
@@ -1072,6 +1077,14 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
                 bulk_prefetch_l2(pfa + (long long)(it + 1u + (unsigned)pfd) * tile_step, (unsigned)(TILE * 8));
                 if (DOT) bulk_prefetch_l2(pfb + (long long)(it + 1u + (unsigned)pfd) * tile_step, (unsigned)(TILE * 8));
             }
+#ifndef EXB_NO_REPROBE_CHECK
+            // A probe that follows a bypass period looks at the exponents first, like the first one: on data that stays
+            // wide (the log-uniform benchmark vector) no tile is ever walked.
+            if (F > 0 && prm.adaptive && bypass == 0 && backoff > kBypassTiles && tile_too_wide<F, DOT, U>(va, vb)) {
+                bypass = backoff;
+                backoff = min(backoff * 16, kBypassMax);
+            }
+#endif
             const bool direct = (F == 0) || (prm.adaptive && bypass > 0);
             int deposits = 0;
             int walked = 0;                                 // expansion levels visited in this tile (warp-uniform)
