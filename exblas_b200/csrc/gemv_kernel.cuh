@@ -369,13 +369,13 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
-                if (has_next) load_group(u);
                 double xb[4];
                 lds128(xaddr, xb[0], xb[1]);
                 lds128(xaddr + 16u, xb[2], xb[3]);
                 xaddr += 32u;
                 double none[1][expansions(0)];
                 mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
+                if (has_next) load_group(u);
             }
             since_norm += 8 * U;
             if (since_norm > kMaxDepositsPerNormalize - 12 * U - 8) {
@@ -499,15 +499,15 @@ EXB_D void mbar_expect_tx(unsigned addr, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
 }
 EXB_D void mbar_wait(unsigned addr, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "EXB_MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra EXB_MBAR_DONE;\n"
-        "bra EXB_MBAR_WAIT;\n"
-        "EXB_MBAR_DONE:\n"
-        "}\n" ::"r"(addr), "r"(parity) : "memory");
+    unsigned done;
+    do {                                                                 // try_wait sleeps in hardware for a while before it gives up
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
 }
 EXB_D void bulk_copy_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
@@ -550,8 +550,13 @@ __device__ __noinline__ void t_issue_chunk(const TPipe tp, const double* x, long
     }
 }
 
+// One column (output) per warp: everything exgemv_t_win_kernel does for one set of columns.  Out of line ON PURPOSE [r2]: inside
+// the kernel's loop over the sets ptxas could not prove that the warp is converged at the top of an iteration (the previous
+// one ends with lane-0-only calls), so every vote in the streaming loop was preceded by a divergence check and every
+// predicated load re-materialised its memory descriptor through R2UR (34 + 17 extra instructions per round of 16
+// products); as a function body the same code is compiled as convergent.  The window travels by value.
 template <int U, int MAXT, int kGemvTChunk>
-__global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams prm) {
+__device__ __noinline__ Window t_column(Window w, const GemvParams& prm, const int set, const unsigned gbase, const unsigned gtotal) {
     // (A variant in which lane l reads rows 4l .. 4l+3 with one 256-bit load was measured slower: its
     // x reads, 32 bytes apart per lane, conflict in shared memory, and the wider requests bought nothing.)
     // here prm.m = number of outputs (columns of A), prm.n = rows summed per output (< 2^31, the host checks),
@@ -561,6 +566,199 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
     // window and its split.  Everything the streaming loop does not need every round lives elsewhere -- the deposit count
     // in w.st (above), the "skip the window" count in the warp's shared-memory slot, 32-bit round counters, the prefetch
     // address derived from the load pointer.
+    extern __shared__ long long smem[];
+    const unsigned T = blockDim.x;                                                   // <= MAXT
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    constexpr unsigned stride = 8u * MAXT;                                           // compile-time limb stride
+    const unsigned col = smem_base + 8u * tid;
+    constexpr unsigned kXsOff = stride * (unsigned)kLimbs;                           // 2 x kGemvTChunk doubles
+    constexpr unsigned kWlOff = kXsOff + 16u * kGemvTChunk;                          // per warp: 39 summed limbs + the skip count
+    constexpr unsigned kCtlOff = kWlOff + (MAXT / 32u) * 320u;                       // the pipeline's mbarriers and counters
+    const unsigned wl_addr = smem_base + kWlOff + (tid >> 5) * 320u;
+    TPipe tp;
+    tp.xs_base = smem_base + kXsOff;
+    tp.ctl = smem_base + kCtlOff;
+    const int nrows = (int)prm.n;
+    const int nwarps = (int)(T >> 5);
+    const int nchunks = (nrows + kGemvTChunk - 1) / kGemvTChunk;
+    const int rounds = nrows / (128 * U);                                            // rounds of U groups of 4 rows per lane, all rows valid
+    constexpr int RPC = kGemvTChunk / (128 * U);                                     // rounds per chunk of x
+    static_assert(RPC * 128 * U == kGemvTChunk && (RPC & (RPC - 1)) == 0, "a chunk of x holds a power of two of whole rounds");
+    // chunk g: wait until it is resident; returns the shared address of this lane's x for the first round of the chunk
+    auto acquire = [&](unsigned g) -> unsigned {
+        mbar_wait(tp.ctl + 8u * (g & 1u), (g >> 1) & 1u);
+        return tp.xs_base + (g & 1u) * (kGemvTChunk * 8u) + 8u * lane;
+    };
+    // chunk g: this warp is done with it; the last warp out refills the buffer with chunk g + 2
+    auto release = [&](unsigned g) {
+        __syncwarp();
+        unsigned old = 0u;
+        asm volatile("fence.acq_rel.cta;" ::: "memory");
+        if (lane == 0u) old = atomicAdd((unsigned*)((char*)smem + kCtlOff + 16u + 4u * (g & 1u)), 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == (unsigned)nwarps - 1u) {
+            if (lane == 0u) *(volatile unsigned*)((char*)smem + kCtlOff + 16u + 4u * (g & 1u)) = 0u;
+            if (g + 2u < gtotal) t_issue_chunk<kGemvTChunk>(tp, prm.x, prm.incx, nrows, nchunks, g + 2u, prm.x_vec_ok);
+        }
+    };
+
+    const double* qa;                                                            // this lane's next group of 4 rows
+    {
+        const long long jraw = (long long)set * nwarps + (tid >> 5);
+        const long long j = jraw < prm.m ? jraw : prm.m - 1;                     // spare warps redo the last column (they take part in the x pipeline)
+        qa = prm.a + j * prm.rs + lane;
+    }
+    double va[U][4];
+    auto load_group = [&](int u) {
+        va[u][0] = ldg64(qa);
+        va[u][1] = ldg64(qa + 32);
+        va[u][2] = ldg64(qa + 64);
+        va[u][3] = ldg64(qa + 96);
+        qa += 128;
+    };
+    auto load_x = [&](unsigned xaddr, double& x0, double& x1, double& x2, double& x3) {
+        x0 = lds_f64(xaddr); x1 = lds_f64(xaddr + 256u); x2 = lds_f64(xaddr + 512u); x3 = lds_f64(xaddr + 768u);
+    };
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (rounds > 0) load_group(u);
+    // L2 prefetch (TMA engine, UBLKPF): at the top of round r the load pointer of lane 0 stands at the first row of round
+    // r + 1, so the 128 U rows that round r + D will read start (D - 1) rounds further on
+    const int pf_dist = prm.l2_prefetch;
+    auto prefetch_round = [&](int r) {
+        if (pf_dist > 0 && lane == 0u && r + pf_dist < rounds) bulk_prefetch_l2(qa + (pf_dist - 1) * (128 * U), 128u * U * 8u);
+    };
+    // top of round r: every RPC rounds hand the finished chunk back and pick up the next one
+    auto chunk_gate = [&](int r) -> unsigned {
+        const unsigned g = gbase + (unsigned)(r / RPC);
+        if (r > 0) release(g - 1u);
+        return acquire(g);
+    };
+    int r = 0;
+    unsigned xaddr = 0u;
+    // ---- loop 1: register window; a warp whose groups keep missing leaves it (for this and the next 7 columns) ----
+    const unsigned skip_window = (unsigned)lds64(wl_addr + 312u);
+    if (__any_sync(0xffffffffu, skip_window > 0u)) {                             // (a vote: the branch is warp-uniform and the compiler knows it)
+        __syncwarp();
+        if (lane == 0u) sts64(wl_addr + 312u, (unsigned long long)(skip_window - 1u));
+    } else {
+        // leaky bucket, warp-uniform (the votes are): +2 per group that missed, -U per round; two rounds in a row
+        // that miss throughout end the loop
+        for (int score = 0; r < rounds && score <= U; ++r) {
+            if ((r & (RPC - 1)) == 0) xaddr = chunk_gate(r);
+            const bool has_next = r + 1 < rounds;
+            prefetch_round(r);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
+                double x0, x1, x2, x3;
+                load_x(xaddr, x0, x1, x2, x3);
+                xaddr += 1024u;
+                const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
+                const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
+                const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
+                const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
+                const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
+                const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
+                if (__all_sync(0xffffffffu, mine)) {
+                    win_add_product(w, p0, __fma_rn(a0, x0, -p0));
+                    win_add_product(w, p1, __fma_rn(a1, x1, -p1));
+                    win_add_product(w, p2, __fma_rn(a2, x2, -p2));
+                    win_add_product(w, p3, __fma_rn(a3, x3, -p3));
+                    w.cnt += 4u;
+                } else {
+                    w = t_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine);
+                    score += 2;
+                }
+                if (has_next) load_group(u);                                     // after the slot's values are dead (see exgemv_n_win_kernel)
+            }
+            score = max(score - U, 0);
+            if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) w = t_flush(w, col, stride);
+        }
+        if (r < rounds) {
+            __syncwarp();
+            if (lane == 0u) sts64(wl_addr + 312u, 7ull);
+        }
+    }
+    // ---- loop 2: wide-range column, every product takes the ordinary path, inlined ----
+    if (r < rounds) {
+        unsigned status = w.st & 0xffffu;
+        int since_norm = (int)(w.st >> 16);
+        for (; r < rounds; ++r) {
+            if ((r & (RPC - 1)) == 0) xaddr = chunk_gate(r);
+            const bool has_next = r + 1 < rounds;
+            prefetch_round(r);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
+                double xb[4];
+                load_x(xaddr, xb[0], xb[1], xb[2], xb[3]);
+                xaddr += 1024u;
+                double none[1][expansions(0)];
+                mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
+                if (has_next) load_group(u);
+            }
+            since_norm += 8 * U;
+            if (since_norm > (int)kTDepLimit - 8 * U) {
+                bound_column(col, stride);
+                since_norm = 0;
+            }
+        }
+        w.st = status | ((unsigned)since_norm << 16);
+    }
+    // rows the full rounds do not cover (fewer than 128 U): they lie in ONE chunk, the last -- which is either the
+    // chunk the last round was in or the one after it
+    {
+        const int r0 = rounds * U * 128;
+        int cur = rounds > 0 ? (rounds - 1) / RPC : -1;                          // chunk this warp holds
+        if (r0 < nrows) {
+            const int chunk = r0 / kGemvTChunk;
+            if (chunk > cur) {
+                if (cur >= 0) release(gbase + (unsigned)cur);
+                (void)acquire(gbase + (unsigned)chunk);
+                cur = chunk;
+            }
+            unsigned status = w.st;                                              // (the count in bits 16.. rides along untouched)
+            double none[1][expansions(0)];
+            const unsigned xb = tp.xs_base + ((gbase + (unsigned)chunk) & 1u) * (kGemvTChunk * 8u);
+            const double* ra = qa;                                               // U * rounds groups have been loaded: this lane's row r0 + lane
+            for (int rr = r0 + (int)lane; rr < nrows; rr += 32, ra += 32) {      // < 4 U rows per lane
+                const double xv = lds_f64(xb + 8u * (unsigned)(rr - chunk * kGemvTChunk));
+                mul_add1<0, false>(col, stride, none, status, ra[0], xv);
+            }
+            w.st = status;
+        }
+        release(gbase + (unsigned)cur);                                          // nrows >= 1: cur is the last chunk, nchunks - 1
+    }
+    // ---- end of the column: drain, warp-sum the 32 private columns, round, store ----
+    w = win_flush_products(w, col, stride);
+    bound_column(col, stride);
+    const unsigned st_all = __reduce_or_sync(0xffffffffu, w.st & 0xffffu);
+    w.st = 0u;
+    for (int jl = 0; jl < kLimbs; ++jl) {
+        const unsigned addr = col + jl * stride;
+        long long v = (long long)lds64(addr);
+        if (__any_sync(0xffffffffu, v != 0)) {
+            sts64(addr, 0ull);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // 32 x (2^52 + 2^11) < 2^58
+        }
+        if (lane == 0) sts64(wl_addr + 8u * (unsigned)jl, (unsigned long long)v);
+    }
+    __syncwarp();
+    {
+        const long long jraw = (long long)set * nwarps + (tid >> 5);
+        if (lane == 0 && jraw < prm.m)
+            gemv_t_store(smem + (kWlOff >> 3) + (size_t)(tid >> 5) * 40, st_all, prm.y + jraw * prm.incy, prm.beta, prm.round_mode,
+                         &prm.ws->status);
+    }
+    __syncwarp();
+    return w;
+}
+
+template <int U, int MAXT, int kGemvTChunk>
+__global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const __grid_constant__ GemvParams prm) {
     extern __shared__ long long smem[];
     const unsigned T = blockDim.x;                                                   // <= MAXT
     const unsigned tid = threadIdx.x, lane = tid & 31u;
@@ -599,180 +797,11 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_t_win_kernel(const GemvParams 
         if (gtotal > 0u) t_issue_chunk<kGemvTChunk>(tp, prm.x, prm.incx, nrows, nchunks, 0u, prm.x_vec_ok);
         if (gtotal > 1u) t_issue_chunk<kGemvTChunk>(tp, prm.x, prm.incx, nrows, nchunks, 1u, prm.x_vec_ok);
     }
-    // chunk g: wait until it is resident; returns the shared address of this lane's x for the first round of the chunk
-    auto acquire = [&](unsigned g) -> unsigned {
-        mbar_wait(tp.ctl + 8u * (g & 1u), (g >> 1) & 1u);
-        return tp.xs_base + (g & 1u) * (kGemvTChunk * 8u) + 8u * lane;
-    };
-    // chunk g: this warp is done with it; the last warp out refills the buffer with chunk g + 2
-    auto release = [&](unsigned g) {
-        __syncwarp();
-        unsigned old = 0u;
-        __threadfence_block();
-        if (lane == 0u) old = atomicAdd((unsigned*)((char*)smem + kCtlOff + 16u + 4u * (g & 1u)), 1u);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old == (unsigned)nwarps - 1u) {
-            if (lane == 0u) *(volatile unsigned*)((char*)smem + kCtlOff + 16u + 4u * (g & 1u)) = 0u;
-            if (g + 2u < gtotal) t_issue_chunk<kGemvTChunk>(tp, prm.x, prm.incx, nrows, nchunks, g + 2u, prm.x_vec_ok);
-        }
-    };
-
     Window w;
     win_reset(w);
     unsigned gbase = 0u;                                                             // sequence number of chunk 0 of the current set
-    for (int set = (int)blockIdx.x; set < nsets; set += (int)gridDim.x, gbase += (unsigned)nchunks) {
-        const double* qa;                                                            // this lane's next group of 4 rows
-        {
-            const long long jraw = (long long)set * nwarps + (tid >> 5);
-            const long long j = jraw < prm.m ? jraw : prm.m - 1;                     // spare warps redo the last column (they take part in the x pipeline)
-            qa = prm.a + j * prm.rs + lane;
-        }
-        double va[U][4];
-        auto load_group = [&](int u) {
-            va[u][0] = ldg64(qa);
-            va[u][1] = ldg64(qa + 32);
-            va[u][2] = ldg64(qa + 64);
-            va[u][3] = ldg64(qa + 96);
-            qa += 128;
-        };
-        auto load_x = [&](unsigned xaddr, double& x0, double& x1, double& x2, double& x3) {
-            x0 = lds_f64(xaddr); x1 = lds_f64(xaddr + 256u); x2 = lds_f64(xaddr + 512u); x3 = lds_f64(xaddr + 768u);
-        };
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (rounds > 0) load_group(u);
-        // L2 prefetch (TMA engine, UBLKPF): at the top of round r the load pointer of lane 0 stands at the first row of round
-        // r + 1, so the 128 U rows that round r + D will read start (D - 1) rounds further on
-        const int pf_dist = prm.l2_prefetch;
-        auto prefetch_round = [&](int r) {
-            if (pf_dist > 0 && lane == 0u && r + pf_dist < rounds) bulk_prefetch_l2(qa + (pf_dist - 1) * (128 * U), 128u * U * 8u);
-        };
-        // top of round r: every RPC rounds hand the finished chunk back and pick up the next one
-        auto chunk_gate = [&](int r) -> unsigned {
-            const unsigned g = gbase + (unsigned)(r / RPC);
-            if (r > 0) release(g - 1u);
-            return acquire(g);
-        };
-        int r = 0;
-        unsigned xaddr = 0u;
-        // ---- loop 1: register window; a warp whose groups keep missing leaves it (for this and the next 7 columns) ----
-        const unsigned skip_window = (unsigned)lds64(wl_addr + 312u);
-        if (skip_window > 0u) {
-            __syncwarp();
-            if (lane == 0u) sts64(wl_addr + 312u, (unsigned long long)(skip_window - 1u));
-        } else {
-            // leaky bucket, warp-uniform (the votes are): +2 per group that missed, -U per round; two rounds in a row
-            // that miss throughout end the loop
-            for (int score = 0; r < rounds && score <= U; ++r) {
-                if ((r & (RPC - 1)) == 0) xaddr = chunk_gate(r);
-                const bool has_next = r + 1 < rounds;
-                prefetch_round(r);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const double a0 = va[u][0], a1 = va[u][1], a2 = va[u][2], a3 = va[u][3];
-                    double x0, x1, x2, x3;
-                    load_x(xaddr, x0, x1, x2, x3);
-                    xaddr += 1024u;
-                    const double p0 = __dmul_rn(a0, x0), p1 = __dmul_rn(a1, x1), p2 = __dmul_rn(a2, x2), p3 = __dmul_rn(a3, x3);
-                    const unsigned k0 = ((unsigned)__double2hiint(p0) & 0x7fffffffu) - w.key0;
-                    const unsigned k1 = ((unsigned)__double2hiint(p1) & 0x7fffffffu) - w.key0;
-                    const unsigned k2 = ((unsigned)__double2hiint(p2) & 0x7fffffffu) - w.key0;
-                    const unsigned k3 = ((unsigned)__double2hiint(p3) & 0x7fffffffu) - w.key0;
-                    const bool mine = max(max(k0, k1), max(k2, k3)) < w.span;
-                    if (__all_sync(0xffffffffu, mine)) {
-                        win_add_product(w, p0, __fma_rn(a0, x0, -p0));
-                        win_add_product(w, p1, __fma_rn(a1, x1, -p1));
-                        win_add_product(w, p2, __fma_rn(a2, x2, -p2));
-                        win_add_product(w, p3, __fma_rn(a3, x3, -p3));
-                        w.cnt += 4u;
-                    } else {
-                        w = t_slow_group(w, col, stride, a0, a1, a2, a3, x0, x1, x2, x3, mine);
-                        score += 2;
-                    }
-                    if (has_next) load_group(u);                                     // after the slot's values are dead (see exgemv_n_win_kernel)
-                }
-                score = max(score - U, 0);
-                if (w.cnt > (unsigned)(kWinFlushEvery - 4 * U)) w = t_flush(w, col, stride);
-            }
-            if (r < rounds) {
-                __syncwarp();
-                if (lane == 0u) sts64(wl_addr + 312u, 7ull);
-            }
-        }
-        // ---- loop 2: wide-range column, every product takes the ordinary path, inlined ----
-        if (r < rounds) {
-            unsigned status = w.st & 0xffffu;
-            int since_norm = (int)(w.st >> 16);
-            for (; r < rounds; ++r) {
-                if ((r & (RPC - 1)) == 0) xaddr = chunk_gate(r);
-                const bool has_next = r + 1 < rounds;
-                prefetch_round(r);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const double xa[4] = {va[u][0], va[u][1], va[u][2], va[u][3]};
-                    if (has_next) load_group(u);
-                    double xb[4];
-                    load_x(xaddr, xb[0], xb[1], xb[2], xb[3]);
-                    xaddr += 1024u;
-                    double none[1][expansions(0)];
-                    mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
-                }
-                since_norm += 8 * U;
-                if (since_norm > (int)kTDepLimit - 8 * U) {
-                    bound_column(col, stride);
-                    since_norm = 0;
-                }
-            }
-            w.st = status | ((unsigned)since_norm << 16);
-        }
-        // rows the full rounds do not cover (fewer than 128 U): they lie in ONE chunk, the last -- which is either the
-        // chunk the last round was in or the one after it
-        {
-            const int r0 = rounds * U * 128;
-            int cur = rounds > 0 ? (rounds - 1) / RPC : -1;                          // chunk this warp holds
-            if (r0 < nrows) {
-                const int chunk = r0 / kGemvTChunk;
-                if (chunk > cur) {
-                    if (cur >= 0) release(gbase + (unsigned)cur);
-                    (void)acquire(gbase + (unsigned)chunk);
-                    cur = chunk;
-                }
-                unsigned status = w.st;                                              // (the count in bits 16.. rides along untouched)
-                double none[1][expansions(0)];
-                const unsigned xb = tp.xs_base + ((gbase + (unsigned)chunk) & 1u) * (kGemvTChunk * 8u);
-                const double* ra = qa;                                               // U * rounds groups have been loaded: this lane's row r0 + lane
-                for (int rr = r0 + (int)lane; rr < nrows; rr += 32, ra += 32) {      // < 4 U rows per lane
-                    const double xv = lds_f64(xb + 8u * (unsigned)(rr - chunk * kGemvTChunk));
-                    mul_add1<0, false>(col, stride, none, status, ra[0], xv);
-                }
-                w.st = status;
-            }
-            release(gbase + (unsigned)cur);                                          // nrows >= 1: cur is the last chunk, nchunks - 1
-        }
-        // ---- end of the column: drain, warp-sum the 32 private columns, round, store ----
-        w = win_flush_products(w, col, stride);
-        bound_column(col, stride);
-        const unsigned st_all = __reduce_or_sync(0xffffffffu, w.st & 0xffffu);
-        w.st = 0u;
-        for (int jl = 0; jl < kLimbs; ++jl) {
-            const unsigned addr = col + jl * stride;
-            long long v = (long long)lds64(addr);
-            if (__any_sync(0xffffffffu, v != 0)) {
-                sts64(addr, 0ull);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // 32 x (2^52 + 2^11) < 2^58
-            }
-            if (lane == 0) sts64(wl_addr + 8u * (unsigned)jl, (unsigned long long)v);
-        }
-        __syncwarp();
-        {
-            const long long jraw = (long long)set * nwarps + (tid >> 5);
-            if (lane == 0 && jraw < prm.m)
-                gemv_t_store(smem + (kWlOff >> 3) + (size_t)(tid >> 5) * 40, st_all, prm.y + jraw * prm.incy, prm.beta, prm.round_mode,
-                             &prm.ws->status);
-        }
-        __syncwarp();
-    }
+    for (int set = (int)blockIdx.x; set < nsets; set += (int)gridDim.x, gbase += (unsigned)nchunks)
+        w = t_column<U, MAXT, kGemvTChunk>(w, prm, set, gbase, gtotal);
 }
 
 // One thread per row: integer sum of the per-part limbs, + beta*y exactly, round, store.
