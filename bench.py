@@ -338,7 +338,7 @@ def run_reference(args, fpes):
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": round(t_step * 1e3, 3),
-        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": config_of(args, world),
         "cpu_baseline": desc,
@@ -739,7 +739,7 @@ def run_ours(args, fpes):
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
-        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": config_of(args, world),
         "shard": {"elements_per_gpu": n, "launches_per_step": launches // max(args.steps, 1),

@@ -686,18 +686,20 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
         p.l2_prefetch = (((uintptr_t)a % 16) == 0 && (rs % 2) == 0) ? (int)h->opt_gemv_prefetch : 0;
         p.x_vec_ok = (incx == 1 && ((uintptr_t)x % 16) == 0 && h->opt_gemv_tma) ? 1 : 0;   // x chunks by cp.async.bulk (else copied by a warp)
         // launch shapes (option "gemv_t_shape"): threads x groups of 4 rows in flight per lane x rows of x per buffer
-        struct TShape { int T, chunk; gemv_fn fn; };
+        struct TShape { int T, chunk, nbuf; gemv_fn fn; };
         static const TShape shapes[] = {
-            {256, 8192, exgemv_t_win_kernel<8, 256, 8192>},
-            {384, 6144, exgemv_t_win_kernel<6, 384, 6144>},
-            {512, 4096, exgemv_t_win_kernel<4, 512, 4096>},
-            {512, 3072, exgemv_t_win_kernel<3, 512, 3072>},
+            {256, 8192, 2, exgemv_t_win_kernel<8, 256, 8192, 2>},
+            {384, 6144, 2, exgemv_t_win_kernel<6, 384, 6144, 2>},
+            {512, 4096, 2, exgemv_t_win_kernel<4, 512, 4096, 2>},
+            {512, 3072, 2, exgemv_t_win_kernel<3, 512, 3072, 2>},
+            {512, 2048, 4, exgemv_t_win_kernel<4, 512, 2048, 4>},
+            {512, 1024, 8, exgemv_t_win_kernel<4, 512, 1024, 8>},
         };
         const TShape& sh = shapes[h->opt_gemv_t_shape];
         const int T = sh.T, nwarps = T / 32, chunk = sh.chunk;
         const int64_t nsets = (m + nwarps - 1) / nwarps;
         const unsigned grid = (unsigned)(nsets < h->num_sms ? nsets : h->num_sms);
-        const size_t smem = ((size_t)T * kLimbs + 2 * (size_t)chunk + 40 * (size_t)nwarps) * sizeof(long long) + 32;   // + the x pipeline's mbarriers / counters
+        const size_t smem = ((size_t)T * kLimbs + (size_t)sh.nbuf * (size_t)chunk + 40 * (size_t)nwarps) * sizeof(long long) + 12 * (size_t)sh.nbuf + 8;   // + the x pipeline's mbarriers / counters
         gemv_fn fn = sh.fn;
         CK(allow_big_smem((const void*)fn, h->device));
         void* args[] = {(void*)&p};
@@ -769,7 +771,7 @@ int gemv_device(exblas_b200_handle_t h, int64_t m, int64_t n, double alpha, cons
     void* args[] = {(void*)&p};
     CK(cudaLaunchKernel((const void*)fn, dim3((unsigned)row_blocks, (unsigned)parts), dim3((unsigned)T), args, smem,
                         h->stream));
-    exgemv_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(p);
+    exgemv_finish_kernel<<<(unsigned)((m + 31) / 32), kFinishT, 0, h->stream>>>(p);
     CK(cudaGetLastError());
     h->launches += 2;
     return EXBLAS_B200_OK;
@@ -1049,7 +1051,7 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
         if (value < 0 || value > 1024) return EXBLAS_B200_EINVAL;   // per-part limbs are bounded by 2^52 + 2^11, not normalised: 1024 of them fit
         h->opt_gemv_parts = value;
     } else if (!strcmp(name, "gemv_t_shape")) {
-        if (value < 0 || value > 3) return EXBLAS_B200_EINVAL;
+        if (value < 0 || value > 5) return EXBLAS_B200_EINVAL;
         h->opt_gemv_t_shape = value;
     } else if (!strcmp(name, "gemv_tma")) {
         h->opt_gemv_tma = value ? 1 : 0;

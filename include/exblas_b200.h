@@ -80,7 +80,10 @@ int exblas_b200_set_stream(exblas_b200_handle_t handle, void* stream);
  * the expansion overflows on most elements; 0 = always walk all fpe levels, as the reference kernels do),
  * "window" (register window of the superaccumulator-only kernels: 0 off, 1 narrow windows, 2 narrow then
  * wide windows (default), 3 wide only), "gemv_n_shape" (0..2) / "gemv_t_shape" (0..3): launch shapes of
- * the ExGEMV window kernels, "fused_allreduce" (1 = exchange limbs inside the kernel once peers are attached),
+ * the ExGEMV window kernels, "gemv_prefetch" (their TMA-engine L2 prefetch distance in rounds, 0 = off, default 2),
+ * "gemv_tma" (ExGEMV 'T': 1 (default) = x is staged by cp.async.bulk whenever it is contiguous and 16-byte aligned,
+ * 0 = always by the copying warp), "reduce_prefetch" (L2 prefetch distance of the expansion kernel in tiles, default 0),
+ * "fused_allreduce" (1 = exchange limbs inside the kernel once peers are attached),
  * "world_size" (declares a multi-rank job: exblas_b200_allreduce_async then fails with EXBLAS_B200_ENCCL
  * instead of finishing locally when no transport covers that many ranks),
  * "peer_timeout_ms" (fused exchange: how long a rank waits for its peers, default 600000, 0 = for ever),

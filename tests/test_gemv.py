@@ -223,7 +223,7 @@ def test_exgemv_t_kernels(gpu, oracle):
                 for alpha, beta in ((1.0, 0.0), (1.0, 1.0), (1.0, -2.5), (0.3, 1.0)):
                     w0 = oracle.exgemv("T", m, n, alpha, a, lda, x[:m], 1, beta, y[:n], 1, 0, False, 0)
                     w1 = oracle.exgemv("T", m, n, alpha, a, lda, x[:m], 1, beta, y[:n], 1, 0, False, 1)
-                    for shape in (0, 1, 2, 3):
+                    for shape in (0, 1, 2, 3, 4, 5):
                         gpu.set_option("gemv_t_shape", shape)
                         for fpe, ee in ((0, False), (8, True)):
                             for rm, want in ((0, w0), (1, w1)):
@@ -242,7 +242,7 @@ def test_exgemv_t_kernels(gpu, oracle):
         ybuf = np.full(offy + (n - 1) * incy + 1, 5.0)
         ybuf[offy::incy][:n] = y[:n]
         want = oracle.exgemv("T", m, n, 1.0, a, lda, x[:m], 1, 1.0, y[:n], 1, 0, False, 0)
-        for shape in (0, 1, 2, 3):
+        for shape in (0, 1, 2, 3, 4, 5):
             gpu.set_option("gemv_t_shape", shape)
             dy = torch.from_numpy(ybuf.copy()).cuda()
             xb.exgemv("T", m, n, 1.0, torch.from_numpy(abuf).cuda(), lda, offa, torch.from_numpy(xbuf).cuda(), incx, offx, 1.0, dy,
@@ -264,6 +264,43 @@ def test_exgemv_t_kernels(gpu, oracle):
         assert np.isinf(out[0]) and np.isnan(out[1]) and np.isfinite(out[2:]).all()
     finally:
         gpu.set_option("gemv_t_shape", 2)
+
+
+@pytest.mark.gpu
+def test_exgemv_t_x_pipeline_many_chunks_and_sets(gpu):
+    """'T' window kernel on a matrix whose columns span several x chunks (with a remainder) and whose outputs need several
+    sets per CTA, so that the TMA / mbarrier pipeline of x wraps around many times: every launch shape, x staged by
+    cp.async.bulk and by the plain-copy fallback (option gemv_tma = 0, and an x that is not 16-byte aligned), must give
+    the bits of the general kernel (option window = 0, checked against the oracle elsewhere)."""
+    import torch
+    import exblas_b200 as xb
+    from exblas_b200 import common as cm
+    rows, cols = 9000 + 77, 148 * 16 * 2 + 5
+    dev = torch.device("cuda:0")
+    for kind in ("narrow", "wide"):
+        er, eo = (10, 5) if kind == "narrow" else (600, 300)
+        A = cm.init_fpuniform(rows * cols, er, eo, seed=11, neg_ratio=2, device=dev)
+        x0 = cm.init_fpuniform(rows, 10, 5, seed=12, neg_ratio=2, device=dev)
+        x1 = torch.zeros(rows + 1, dtype=torch.float64, device=dev)
+        x1[1:] = x0                                         # the same x, one element (8 bytes) further on
+        y0 = cm.init_fpuniform(cols, 100, 50, seed=13, neg_ratio=2, device=dev)
+        try:
+            gpu.set_option("window", 0)
+            want = y0.clone()
+            xb.exgemv("T", rows, cols, 1.0, A, rows, 0, x0, 1, 0, 1.0, want, 1, 0, 0, False, handle=gpu)
+            gpu.set_option("window", 2)
+            for shape in (0, 1, 2, 3, 4, 5):
+                gpu.set_option("gemv_t_shape", shape)
+                for tma, offx in ((1, 0), (0, 0), (1, 1)):
+                    gpu.set_option("gemv_tma", tma)
+                    got = y0.clone()
+                    xb.exgemv("T", rows, cols, 1.0, A, rows, 0, x1 if offx else x0, 1, offx, 1.0, got, 1, 0, 3, False, handle=gpu)
+                    assert bool((got.view(torch.int64) == want.view(torch.int64)).all()), (kind, shape, tma, offx)
+                    assert gpu.last_status() == 0
+        finally:
+            gpu.set_option("window", 2)
+            gpu.set_option("gemv_t_shape", 2)
+            gpu.set_option("gemv_tma", 1)
 
 
 @pytest.mark.gpu
