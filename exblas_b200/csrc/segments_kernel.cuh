@@ -176,19 +176,27 @@ __global__ void __launch_bounds__(MAXT, 2) exblas_segments_kernel(const __grid_c
     Window w;
     win_reset(w);
     int skip_window = 0;                                              // pieces left to run without the register window
+    // The segment bounds are read 32 at a time: lane k keeps seg[cbase + k] and seg[cbase + k + 1], and the bounds of the
+    // segment at hand come out of that cache by shuffle -- read one by one they were two or three DEPENDENT global loads
+    // per segment, most of the time of segments of a few hundred elements.
+    long long cl0 = 0, cl1 = 0, cbase = -64;
+    auto load_bounds = [&](long long at) {
+        const long long i0 = at + lane < nseg ? at + lane : nseg, i1 = at + lane + 1 < nseg ? at + lane + 1 : nseg;
+        cl0 = prm.seg[i0];
+        cl1 = prm.seg[i1];
+        cbase = at;
+    };
     while (s < nseg) {
-        const long long b0 = prm.seg[s];
+        if (s - cbase >= 32) load_bounds(s);
+        const long long b0 = __shfl_sync(kFullWarp, cl0, (int)(s - cbase));
         if (b0 >= end && !(last_range && b0 == N1)) break;            // starts in a later range
         // ---------------- lane-per-segment mode: up to 32 short segments that lie inside this range ----------------
-        {
+        if (__shfl_sync(kFullWarp, cl1, (int)(s - cbase)) - b0 <= kSegShort) {
+            if (s != cbase) load_bounds(s);                           // a full batch of 32 candidates
             const long long sl = s + lane;
-            long long l0 = 0, l1 = 0;
+            const long long l0 = cl0, l1 = cl1;
             bool ok = false;
-            if (sl < nseg) {
-                l0 = prm.seg[sl];
-                l1 = prm.seg[sl + 1];
-                ok = l0 >= start && l1 <= end && l1 - l0 <= kSegShort && (l0 < end || (last_range && l0 == N1));
-            }
+            if (sl < nseg) ok = l0 >= start && l1 <= end && l1 - l0 <= kSegShort && (l0 < end || (last_range && l0 == N1));
             const unsigned okm = __ballot_sync(kFullWarp, ok);
             const int batch = (okm == 0xffffffffu) ? 32 : __ffs((int)~okm) - 1;   // leading run of short, complete segments
             if (batch >= 4) {
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(MAXT, 2) exblas_segments_kernel(const __grid_c
             }
         }
         // ---------------- warp mode: this warp's piece [lo, hi) of segment s ----------------
-        const long long b1 = prm.seg[s + 1];
+        const long long b1 = __shfl_sync(kFullWarp, cl1, (int)(s - cbase));
         const long long lo = b0 > start ? b0 : start, hi = b1 < end ? b1 : end;
         const long long n = hi > lo ? hi - lo : 0;
         const long long full = n / 128;                               // groups in which every lane has 4 elements
@@ -343,30 +351,50 @@ __global__ void __launch_bounds__(MAXT, 2) exblas_segments_kernel(const __grid_c
         WarpLimbs x;
         x.a = 0;
         x.b = 0;
-        long long carry_prev = 0;                                     // carry-save part of the row below
-#pragma unroll 1
-        for (int jl = 0; jl < kLimbs; ++jl) {
-            const unsigned addr = col + jl * stride;
-            const long long v = (long long)lds64(addr);
-            long long rowsum = carry_prev;
-            carry_prev = 0;
-            if (__any_sync(0xffffffffu, v != 0)) {
-                sts64(addr, 0ull);
-                const unsigned long long vlo = (unsigned long long)(v & kLimbMask);
-                const unsigned r0 = __reduce_add_sync(kFullWarp, (unsigned)vlo & 0x3ffffu);            // 3 x 18 bits: 32 lane sums < 2^23
-                const unsigned r1 = __reduce_add_sync(kFullWarp, (unsigned)(vlo >> 18) & 0x3ffffu);
-                const unsigned r2 = __reduce_add_sync(kFullWarp, (unsigned)(vlo >> 36));
-                const int rh = __reduce_add_sync(kFullWarp, (int)(v >> kDigits));
-                rowsum += (long long)((unsigned long long)r0 + ((unsigned long long)r1 << 18) + ((unsigned long long)r2 << 36));
-                if (jl == kLimbs - 1) rowsum += ((long long)rh) << kDigits;      // the top limb keeps its own carry-save bits
-                else carry_prev = rh;
-            }
-            if (jl < 32) {
-                if ((int)lane == jl) x.a = rowsum;
-            } else if ((int)lane == jl - 32) {
-                x.b = rowsum;
-            }
+        // which rows has any lane touched?  13 independent loads per step and ONE warp reduction of the 13 flags (a row at a
+        // time this scan was a chain of 39 dependent load -> vote -> branch steps, ~2000 cycles per piece: for segments of a
+        // few hundred elements most of the time)
+        unsigned long long touched = 0ull;
+#pragma unroll
+        for (int b3 = 0; b3 < 3; ++b3) {
+            unsigned m = 0u;
+#pragma unroll
+            for (int q = 0; q < 13; ++q) m |= lds64(col + (unsigned)(13 * b3 + q) * stride) != 0ull ? (1u << q) : 0u;
+            touched |= (unsigned long long)__reduce_or_sync(kFullWarp, m) << (13 * b3);
         }
+        auto place = [&](int j, long long v) {                        // limb j of the sum lives in lane j (.a) / lane j - 32 (.b)
+            if (j < 32) {
+                if ((int)lane == j) x.a = v;
+            } else if ((int)lane == j - 32) {
+                x.b = v;
+            }
+        };
+        long long carry_prev = 0;                                     // carry-save part of row `prev`: belongs to row prev + 1
+        int prev = -2;
+        while (touched) {
+            const int jl = __ffsll((long long)touched) - 1;
+            touched &= touched - 1ull;
+            if (carry_prev != 0 && prev + 1 != jl) place(prev + 1, carry_prev);   // an untouched row receives the carry alone
+            const unsigned addr = col + (unsigned)jl * stride;
+            const long long v = (long long)lds64(addr);
+            sts64(addr, 0ull);
+            const unsigned long long vlo = (unsigned long long)(v & kLimbMask);
+            const unsigned r0 = __reduce_add_sync(kFullWarp, (unsigned)vlo & 0x3ffffu);            // 3 x 18 bits: 32 lane sums < 2^23
+            const unsigned r1 = __reduce_add_sync(kFullWarp, (unsigned)(vlo >> 18) & 0x3ffffu);
+            const unsigned r2 = __reduce_add_sync(kFullWarp, (unsigned)(vlo >> 36));
+            const int rh = __reduce_add_sync(kFullWarp, (int)(v >> kDigits));
+            long long rowsum = (long long)((unsigned long long)r0 + ((unsigned long long)r1 << 18) + ((unsigned long long)r2 << 36));
+            if (prev + 1 == jl) rowsum += carry_prev;
+            if (jl == kLimbs - 1) {
+                rowsum += ((long long)rh) << kDigits;                 // the top limb keeps its own carry-save bits
+                carry_prev = 0;
+            } else {
+                carry_prev = rh;
+            }
+            place(jl, rowsum);
+            prev = jl;
+        }
+        if (carry_prev != 0) place(prev + 1, carry_prev);             // (prev < 38 here: the top row leaves no carry)
         const bool complete = b0 >= start && b1 <= end;
         if (complete) {
             seg_finish(prm, x, st_all, s, lane);
