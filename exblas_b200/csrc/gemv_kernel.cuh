@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_kernel(const GemvParams prm)
         if constexpr (unit_alpha) {
             if (direct) {
                 double none[1][expansions(0)];
-                mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
+                mul_add4<0, false, true, true>(col, stride, none, status, xa, xb);
             } else {
                 deposits += mul_add4<F, EE, true>(col, stride, a, status, xa, xb);
             }
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(MAXT, 1) exgemv_n_win_kernel(const GemvParams 
                 lds128(xaddr + 16u, xb[2], xb[3]);
                 xaddr += 32u;
                 double none[1][expansions(0)];
-                mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
+                mul_add4<0, false, true, true>(col, stride, none, status, xa, xb);
                 if (has_next) load_group(u);
             }
             since_norm += 8 * U;
@@ -666,7 +666,7 @@ __device__ __noinline__ Window t_column(Window w, const GemvParams& prm, const i
                 load_x(xaddr, xb[0], xb[1], xb[2], xb[3]);
                 xaddr += 1024u;
                 double none[1][expansions(0)];
-                mul_add4<0, false, true, false>(col, stride, none, status, xa, xb);
+                mul_add4<0, false, true, true>(col, stride, none, status, xa, xb);
                 if (has_next) load_group(u);
             }
             since_norm += 8 * U;
