@@ -304,6 +304,44 @@ def test_exgemv_t_x_pipeline_many_chunks_and_sets(gpu):
 
 
 @pytest.mark.gpu
+def test_exgemv_t_random_shapes_against_general_kernel(gpu):
+    """'T' window kernel against the general kernel (option window = 0) on random shapes around the chunk and round
+    boundaries of every launch shape: odd row counts, single columns, padded leading dimensions, beta != 0."""
+    import torch
+    import exblas_b200 as xb
+    from exblas_b200 import common as cm
+    rng = np.random.default_rng(2024)
+    dev = torch.device("cuda:0")
+    edges = [256, 257, 383, 384, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 3071, 3072, 3073, 4095, 4096, 4097, 6143, 6144, 6145,
+             8191, 8192, 8193, 12287, 12289, 16385]
+    try:
+        for t in range(24):
+            rows = int(edges[t % len(edges)] if t < 16 else rng.integers(256, 20000))
+            cols = int(rng.choice([1, 2, 15, 16, 17, 33, 150]))
+            lda = rows + int(rng.integers(0, 5))
+            A = cm.init_fpuniform(lda * cols, 40, 20, seed=100 + t, neg_ratio=2, device=dev)
+            x = cm.init_fpuniform(rows, 10, 5, seed=200 + t, neg_ratio=2, device=dev)
+            y0 = cm.init_fpuniform(cols, 30, 15, seed=300 + t, neg_ratio=2, device=dev)
+            beta = float(rng.choice([0.0, 1.0, -0.75]))
+            gpu.set_option("window", 0)
+            want = y0.clone()
+            xb.exgemv("T", rows, cols, 1.0, A, lda, 0, x, 1, 0, beta, want, 1, 0, 0, False, handle=gpu)
+            gpu.set_option("window", 2)
+            for shape in (0, 1, 2, 3, 4, 5):
+                gpu.set_option("gemv_t_shape", shape)
+                for tma in (1, 0):
+                    gpu.set_option("gemv_tma", tma)
+                    got = y0.clone()
+                    xb.exgemv("T", rows, cols, 1.0, A, lda, 0, x, 1, 0, beta, got, 1, 0, 0, False, handle=gpu)
+                    assert bool((got.view(torch.int64) == want.view(torch.int64)).all()), (rows, cols, lda, beta, shape, tma)
+            assert gpu.last_status() == 0
+    finally:
+        gpu.set_option("window", 2)
+        gpu.set_option("gemv_t_shape", 2)
+        gpu.set_option("gemv_tma", 1)
+
+
+@pytest.mark.gpu
 def test_exgemv_exact_scaling_domain_is_flagged(gpu):
     """alpha * a[i, j] / beta * y[i] that cannot be split exactly into two doubles are dropped and flagged, never summed
     inexactly (include/exblas_b200.h: domain of the exact scaling)."""
