@@ -243,6 +243,7 @@ struct exblas_b200_handle_s {
     int64_t opt_gemv_t_shape = 2;
     int64_t opt_gemv_n_shape = 1;
     int64_t opt_reduce_prefetch = 0;        // expansion kernel: L2 bulk-prefetch distance in tiles (0 = off)
+    int64_t opt_track_max = (int64_t)1 << 20;   // ExSUM vectors up to this length: superaccumulator-only kernel, no unrolled body, touched rows only
     int64_t opt_gemv_tma = 1;               // ExGEMV 'T': stage x with TMA bulk copies (0 = plain copies by a warp; for A/B and tests)
     int64_t opt_gemv_prefetch = 2;          // ExGEMV window kernels: L2 bulk-prefetch distance in rounds (0 = off)
     int64_t opt_window = 2;                 // register window in the superaccumulator-only kernels (performance only)
@@ -398,6 +399,17 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
         h->last_kernel = std::string(dot ? "exblas_small_kernel<DOT=1>" : "exblas_small_kernel<DOT=0>") + " grid=1 block=" + std::to_string(T);
         return EXBLAS_B200_OK;
     }
+    // Mid sizes (ExSUM up to "track_max_elems", default 2^20): what such a launch costs is its fixed part, and the cheapest
+    // fixed part is the superaccumulator-only kernel WITHOUT its unrolled body -- every summand then passes through the
+    // loops of reduce_finish that record the exponent range, so the merge sums only the limb rows that were touched (the
+    // analogue of the reference's imin / imax).  Measured in graph replay for 2^14 ... 2^20 elements, narrow and wide data:
+    // 7.1-10.2 us against 8.3-14.1 us for the kernels fpe would select (profiles/track_sweep_r02.jsonl).  Every fpe value
+    // takes it: fpe never changes a result.
+    const bool mid = !h->opt_shape_fixed && !dot && n <= h->opt_track_max;
+    if (mid) {
+        f = 0;
+        ee = false;
+    }
     if (!h->opt_shape_fixed && n <= h->opt_small_max) T = 256;
     int64_t blocks = (work + 4 * (int64_t)T - 1) / (4 * (int64_t)T);   // four vectors per thread keep the loads overlapped
     if (blocks < 1) blocks = 1;
@@ -406,6 +418,7 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     const int U = f == 0 ? 1 : vectors_in_flight(f, ee, dot);     // exblas_reduce0_kernel tiles by rows of T * 4 elements
     p.iters = p.nvec / ((int64_t)T * U * blocks);
     if (p.iters > 0x7fffffff) p.iters = 0x7fffffff;               // (2^31 tiles per CTA: beyond any memory)
+    if (mid) p.iters = 0;
     if (h->d_phase) h->phase_blocks = (int)blocks;
 
     // superaccumulator-only mode: window loop with 6 (ExSUM) / 2 (ExDOT) rows in flight, direct loop with 8 / 4
@@ -1053,6 +1066,8 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "gemv_t_shape")) {
         if (value < 0 || value > 5) return EXBLAS_B200_EINVAL;
         h->opt_gemv_t_shape = value;
+    } else if (!strcmp(name, "track_max_elems")) {
+        h->opt_track_max = value;
     } else if (!strcmp(name, "gemv_tma")) {
         h->opt_gemv_tma = value ? 1 : 0;
     } else if (!strcmp(name, "reduce_prefetch")) {

@@ -73,7 +73,9 @@ int exblas_b200_set_stream(exblas_b200_handle_t handle, void* stream);
 /* Tuning knobs (performance only, never the result): "block_threads" (multiple of 32, <= 512) and
  * "blocks" (0 = automatic) fix the launch shape by hand ("auto_shape" = 1 returns to the size-dependent
  * one: a single CTA up to "solo_max_elems" elements, 256-thread CTAs up to "small_max_elems", else one
- * 512-thread CTA per SM), "host_chunk_elems" (elements per H2D chunk of pinned host input), "host_threads" /
+ * 512-thread CTA per SM), "track_max_elems" (ExSUM vectors up to this length, default 2^20, take the superaccumulator-only
+ * kernel without its unrolled body whatever fpe says: it merges only the limb rows it touched, the cheapest launch at
+ * those sizes; 0 = the kernel fpe selects), "host_chunk_elems" (elements per H2D chunk of pinned host input), "host_threads" /
  * "pageable_chunk_elems" (pageable host input goes through pinned bounce buffers filled by that many copy
  * threads, 0 = automatic, 1 = none: the driver's own pageable staging), "gemv_parts" (0 = automatic column split, <= 1024),
  * "adaptive" (1 = a warp bypasses the expansion and deposits straight into its superaccumulators while
