@@ -1523,9 +1523,11 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce0_kernel(const __grid_co
                     if (prm.window != 3)
                         k = reduce0_window_rows_wide<DW, 3>(pa0, pb0, row_step, iters, col, stride, &st1, range);
                     if (k < iters && prm.window > 1)
-                        // (two rows in flight, refilled BEFORE the row is consumed: measured best of 2 / 3 / 4 rows, early / late
-                        // refill: 6.7 against 5.0-6.4 TB/s on ill-conditioned data; the wide loop spends ~45 instructions per product)
-                        k += reduce0_window_rows_wide<DW, 5, true>(pa0 + (long long)k * row_step, pb0 + (long long)k * row_step, row_step,
+                        // (three rows in flight, each slot refilled AFTER its row is consumed: 5.3 TB/s sustained on the ill-conditioned
+                        // pair against 5.2 / 5.1 / 4.8 for 2 / 4 / 1 rows and 4.75 for two rows refilled BEFORE the row is consumed --
+                        // profiles/ab_w5_r02.jsonl.  Called from this kernel the function has ~30 registers less than on its own:
+                        // the early refill, once the best, now spills its load slots; the wide loop spends ~45 instructions per product)
+                        k += reduce0_window_rows_wide<3, 5, false>(pa0 + (long long)k * row_step, pb0 + (long long)k * row_step, row_step,
                                                                    iters - k, col, stride, &st1, range);
                 } else {
                     if (prm.window != 3)

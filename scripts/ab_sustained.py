@@ -37,6 +37,8 @@ def child(cfgs, seconds, log2n):
             elif kind == "logu": cache[kind] = (sliced(lambda lo, hi: cm.init_fpuniform(n, 664, 332, seed=1, neg_ratio=2, lo=lo, hi=hi, device=dev)), None)
             elif kind == "naive": cache[kind] = (cm.init_naive(n, device=dev), None)
             elif kind == "ill": cache[kind] = cm.cancelling_pair(n, "dot", seed=7, device=dev)
+            elif kind == "narrow": cache[kind] = (sliced(lambda lo, hi: cm.init_fpuniform(n, 10, 5, seed=1, neg_ratio=2, lo=lo, hi=hi, device=dev)),
+                                                  sliced(lambda lo, hi: cm.init_fpuniform(n, 10, 5, seed=2, neg_ratio=2, lo=lo, hi=hi, device=dev)))
             elif kind == "illsum": cache[kind] = (sliced(lambda lo, hi: cm.init_ill_cond(n, 1e32, seed=1, lo=lo, hi=hi, device=dev)), None)
         return cache[kind]
 
