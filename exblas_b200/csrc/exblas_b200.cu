@@ -244,6 +244,7 @@ struct exblas_b200_handle_s {
     int64_t opt_gemv_n_shape = 1;
     int64_t opt_reduce_prefetch = 0;        // expansion kernel: L2 bulk-prefetch distance in tiles (0 = off)
     int64_t opt_track_max = (int64_t)1 << 20;   // ExSUM vectors up to this length: superaccumulator-only kernel, no unrolled body, touched rows only
+    int64_t opt_dot_handoff = 16;           // ExDOT expansion kernels: tiles per CTA from which a thrashing warp hands its rows to the 5-digit window loop (0 = never)
     int64_t opt_gemv_tma = 1;               // ExGEMV 'T': stage x with TMA bulk copies (0 = plain copies by a warp; for A/B and tests)
     int64_t opt_gemv_prefetch = 2;          // ExGEMV window kernels: L2 bulk-prefetch distance in rounds (0 = off)
     int64_t opt_window = 2;                 // register window in the superaccumulator-only kernels (performance only)
@@ -384,6 +385,7 @@ int launch_reduce(exblas_b200_handle_t h, bool dot, int f, bool ee, const double
     p.peer_timeout_ns = (unsigned long long)h->opt_peer_timeout_ms * 1000000ull;
     p.phase = h->d_phase;
     p.l2_prefetch = (int)h->opt_reduce_prefetch;
+    p.handoff_tiles = (int)h->opt_dot_handoff;
     if (!h->opt_shape_fixed && n <= h->opt_solo_max && p.fresh && finalize) {
         // latency regime: the small single-CTA kernel (every fpe value: fpe never changes the result)
         const int64_t per_thread4 = p.nvec > 0 ? (p.nvec + 3) / 4 : (n + 3) / 4;
@@ -1066,6 +1068,9 @@ int exblas_b200_set_option(exblas_b200_handle_t h, const char* name, int64_t val
     } else if (!strcmp(name, "gemv_t_shape")) {
         if (value < 0 || value > 5) return EXBLAS_B200_EINVAL;
         h->opt_gemv_t_shape = value;
+    } else if (!strcmp(name, "dot_handoff_tiles")) {
+        if (value < 0 || value > 0x7fffffff) return EXBLAS_B200_EINVAL;
+        h->opt_dot_handoff = value;
     } else if (!strcmp(name, "track_max_elems")) {
         h->opt_track_max = value;
     } else if (!strcmp(name, "gemv_tma")) {

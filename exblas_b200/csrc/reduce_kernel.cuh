@@ -89,6 +89,7 @@ struct ReduceParams {
     unsigned long long epoch;            // identifies this collective reduction (same on every rank, >= 1)
     unsigned long long peer_timeout_ns;  // give up waiting for a peer after this long (0 = wait for ever)
     int l2_prefetch;                     // expansion kernel: bulk L2 prefetch distance in tiles (0 = off; performance only)
+    int handoff_tiles;                   // ExDOT expansion kernels: hand a thrashing vector of at least this many tiles per CTA to the 5-digit window loop (0 = never)
     unsigned long long* phase;           // optional [gridDim.x][kPhaseSlots] globaltimer stamps (nullptr = off)
 };
 
@@ -980,6 +981,39 @@ EXB_D void reduce_finish(const ReduceParams& prm, const unsigned col, const unsi
     block_merge_and_close(prm, stride, smem_base, T, tid, status, solo, block_lo, block_hi, block_status, row_lo, row_hi);
 }
 
+// (defined further down, with the superaccumulator-only kernel)
+template <int DW, int W, bool EARLY>
+__device__ __noinline__ unsigned reduce0_window_rows_wide(const double* pa, const double* pb, const long long row_step,
+                                                          const unsigned iters, const unsigned col, const unsigned stride, unsigned* status_io, int* range_io);
+
+// Hand-off of the ExDOT expansion kernels [r2]: products that thrash an expansion but fit the 5-digit register window
+// (ill-conditioned dot products: ~125 binades) stream faster through that window than through direct deposits (6.1 against
+// 5.2-5.5 TB/s), and fpe never changes the result.  A warp whose first tile thrashed hands the REST of its rows (the ExDOT
+// tiles are rows of the superaccumulator-only kernel's geometry, so a thread's vectors form one arithmetic progression) to
+// that kernel's window loop; rows the loop leaves (the window no longer fits) are deposited directly.  Out of line: the
+// streaming loops of the kernel must not pay for this code with registers.  Returns status flags; the column is bounded.
+__device__ __noinline__ unsigned dot_handoff(const double* qa, const double* qb, const long long row_step, const unsigned rows,
+                                             const unsigned col, const unsigned stride) {
+    unsigned status = 0;
+    bound_column(col, stride);
+    int range[2] = {4096, -4096};
+    unsigned k = reduce0_window_rows_wide<3, 5, false>(qa, qb, row_step, rows, col, stride, &status, range);
+    int since_norm = 0;
+    for (; k < rows; ++k) {                                                      // (rare: the window gave up on the way)
+        const Vec4 xa = ldg256(qa + (long long)k * row_step), xb = ldg256(qb + (long long)k * row_step);
+        const double x[4] = {xa.x, xa.y, xa.z, xa.w}, y[4] = {xb.x, xb.y, xb.z, xb.w};
+        double none[1][expansions(0)];
+        mul_add4<0, false, false>(col, stride, none, status, x, y);
+        since_norm += 8;
+        if (since_norm > kMaxDepositsPerNormalize - 64) {
+            bound_column(col, stride);
+            since_norm = 0;
+        }
+    }
+    bound_column(col, stride);
+    return status;
+}
+
 // True when the exponents of the tile a warp holds in registers span more than an F-level expansion can hold (53 F bits
 // plus slack): such a tile is not worth walking.  Warp-uniform.
 template <int F, bool DOT, int U>
@@ -1032,16 +1066,21 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
     const long long TILE = (long long)T * 4 * U;
     int since_norm = 0;
     bool bypass_hint = false;
+    bool handed_off = false;
 
     // ---------------- vector body: prm.iters full tiles per CTA, 256-bit loads, rolling prefetch ----------------
     // (every CTA streams the same number of tiles: tiles blockIdx.x, blockIdx.x + grid, ...; what that leaves over
     // is spread evenly over all threads by reduce_finish)
     if (prm.iters > 0) {
         const unsigned iters = (unsigned)prm.iters;
-        const long long tile_step = (long long)gridDim.x * TILE;               // elements between my tiles
-        const double* pa = prm.a + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4;
-        const double* pb = DOT ? prm.b + prm.head + (long long)blockIdx.x * TILE + (long long)tid * 4 : nullptr;
-        const long long vstep = (long long)T * 4;                               // elements between my vectors
+        // ExSUM: a tile is T * U consecutive vectors.  ExDOT: a tile is U ROWS of T vectors, grid * T vectors apart (the
+        // geometry of the superaccumulator-only kernel), so that the vectors a thread owns form ONE arithmetic progression
+        // and a warp can hand its rest to that kernel's window loop on its own (see the hand-off below).
+        const long long vstep = DOT ? (long long)gridDim.x * T * 4 : (long long)T * 4;      // elements between my vectors
+        const long long tile_step = DOT ? (long long)U * vstep : (long long)gridDim.x * TILE;   // elements between my tiles
+        const long long first = DOT ? (long long)blockIdx.x * T * 4 : (long long)blockIdx.x * TILE;
+        const double* pa = prm.a + prm.head + first + (long long)tid * 4;
+        const double* pb = DOT ? prm.b + prm.head + first + (long long)tid * 4 : nullptr;
         Vec4 va[U];
         Vec4 vb[DOT ? U : 1];
 #pragma unroll
@@ -1052,7 +1091,7 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
         // clear the (thread-private: no barrier needed) column while the first loads are in flight
         for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
         // TMA-engine L2 prefetch of whole tiles (one UBLKPF per tile and stream, thread 0): D tiles ahead of the loads
-        const int pfd = prm.l2_prefetch;
+        const int pfd = DOT ? 0 : prm.l2_prefetch;                              // (contiguous tiles only)
         const double* pfa = prm.a + prm.head + (long long)blockIdx.x * TILE;
         const double* pfb = DOT ? prm.b + prm.head + (long long)blockIdx.x * TILE : nullptr;
         if (pfd > 0 && tid == 0) {
@@ -1065,9 +1104,15 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
         // The first probe of the expansion is skipped when the exponents of the first tile alone span more than an
         // F-level expansion can hold (log-uniform 2^+-332 against 53 F bits): walking a thrashing tile costs ~10 direct
         // tiles, which vectors of 2^22..2^26 elements never amortise.  Later probes (after a bypass period) are real.
+#ifdef EXB_NO_HANDOFF
+        bool handoff_ok = false;
+#else
+        bool handoff_ok = DOT && F > 0 && prm.adaptive && prm.window > 1 && prm.handoff_tiles > 0 && iters >= (unsigned)prm.handoff_tiles;
+#endif
         if (F > 0 && prm.adaptive && tile_too_wide<F, DOT, U>(va, vb)) {
             bypass = backoff;
             backoff = min(backoff * 16, kBypassMax);
+            handoff_ok = false;                                // wider than any window: the direct tiles below are the right path
         }
         for (unsigned it = 0; it < iters; ++it) {
             pa += tile_step;
@@ -1172,8 +1217,22 @@ __global__ void __launch_bounds__(MAXT, 1) exblas_reduce_kernel(const __grid_con
                 bound_column(col, stride);
                 since_norm = 0;
             }
+            if (DOT && F > 0 && it == 0u && handoff_ok && bypass > 0) {   // (never with EXB_NO_HANDOFF)
+                handed_off = true;                             // the first tile thrashed the expansion (warp-uniform)
+                break;
+            }
         }
         bypass_hint = bypass > 0;
+#ifndef EXB_NO_HANDOFF
+        if constexpr (DOT && F > 0) {
+            if (handed_off) {
+                status |= dot_handoff(prm.a + prm.head + (long long)blockIdx.x * T * 4 + (long long)tid * 4 + (long long)U * vstep,
+                                      prm.b + prm.head + (long long)blockIdx.x * T * 4 + (long long)tid * 4 + (long long)U * vstep, vstep,
+                                      (iters - 1u) * (unsigned)U, col, stride);
+                since_norm = 0;
+            }
+        }
+#endif
     } else {
         for (int j = 0; j < kLimbs; ++j) sts64(col + j * stride, 0ull);
     }

@@ -80,6 +80,8 @@ int exblas_b200_set_stream(exblas_b200_handle_t handle, void* stream);
  * threads, 0 = automatic, 1 = none: the driver's own pageable staging), "gemv_parts" (0 = automatic column split, <= 1024),
  * "adaptive" (1 = a warp bypasses the expansion and deposits straight into its superaccumulators while
  * the expansion overflows on most elements; 0 = always walk all fpe levels, as the reference kernels do),
+ * "dot_handoff_tiles" (ExDOT with fpe >= 3: a warp whose first tile thrashes the expansion hands the rest of its rows to
+ * the 5-digit register window when the vector gives every CTA at least this many tiles, default 16, 0 = never),
  * "window" (register window of the superaccumulator-only kernels: 0 off, 1 narrow windows, 2 narrow then
  * wide windows (default), 3 wide only), "gemv_n_shape" (0..2) / "gemv_t_shape" (0..3): launch shapes of
  * the ExGEMV window kernels, "gemv_prefetch" (their TMA-engine L2 prefetch distance in rounds, 0 = off, default 2),

@@ -232,6 +232,29 @@ def test_small_and_mid_sizes_every_shape_regime(gpu, oracle):
             assert same_double(v, w) and (l == wl).all(), ("sum+1", n)
 
 
+def test_exdot_handoff_to_the_window_loop(gpu, oracle):
+    """ExDOT with fpe >= 3: a warp whose first tile thrashes the expansion hands the rest of its rows to the 5-digit window
+    loop (option dot_handoff_tiles; default 16 tiles per CTA, here 1 so that vectors of a few million elements take it).
+    Ill-conditioned products (the case it is for), wide-range products (too wide for any window: no hand-off) and narrow
+    ones (no thrashing: no hand-off) must all give the oracle's value and limbs, with and without the hand-off."""
+    nmax = 3 * (1 << 21) + 4111
+    pairs = {"illcond": (cm.init_ill_cond(nmax, 1e32, seed=31), cm.init_ill_cond(nmax, 1e32, seed=32)),
+             "wide": (cm.init_fpuniform(nmax, 664, 332, seed=33, neg_ratio=2), cm.init_fpuniform(nmax, 200, 100, seed=34, neg_ratio=2)),
+             "narrow": (cm.init_fpuniform(nmax, 10, 5, seed=35, neg_ratio=2), cm.init_fpuniform(nmax, 10, 5, seed=36, neg_ratio=2))}
+    try:
+        for kind, (a, b) in pairs.items():
+            da, db = dev(a), dev(b)
+            for n in ((1 << 21) + 5, 1 << 22, nmax):
+                d0, dl0 = oracle.exdot(a[:n], b[:n], fpe=0)
+                for handoff in (1, 0):
+                    gpu.set_option("dot_handoff_tiles", handoff)
+                    for fpe, ee in [(3, False), (4, False), (8, False), (6, True), (8, True)]:
+                        v, l = gpu.exdot(n, da, 1, 0, db, 1, 0, fpe, ee, want_limbs=True)
+                        assert same_double(v, d0) and (l == dl0).all(), (kind, n, handoff, fpe, ee)
+    finally:
+        gpu.set_option("dot_handoff_tiles", 16)
+
+
 def test_partial_sums_near_the_top_of_the_layout(gpu):
     """Inputs below 2^988 whose partial sums inside one expansion exceed it: every fpe must give the exact sum
     (the expansion flush adds such a partial sum to limb 38 as an integer)."""
